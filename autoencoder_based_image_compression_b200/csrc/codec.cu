@@ -1,0 +1,708 @@
+// Codec handle: weights re-laid-out for the kernels, layer plans for the analysis / synthesis
+// transforms (kodak_tensorflow/eae/graph/components.py:11-142) and the fused
+// encode -> quantize -> lossless code -> container pipeline and its inverse.
+#include <memory>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_plan.cuh"
+#include "internal.cuh"
+#include "transforms.cuh"
+
+using namespace eae;
+
+struct eae_codec {
+    int device = 0;
+    int learned = 0;   // are_bin_widths_learned: 4 GDN/IGDN instead of 6
+    int math = EAE_MATH_FP32_SIMT;
+    cudaStream_t own_stream = nullptr;
+
+    // ---- weights (device) ----
+    DevBuf w1m;            // [96][128]   im2col matrix of weights_1 (rows >= 81 are zero)
+    DevBuf w2, w3;         // [25][128 in][128 out]  = TF [kh,kw,in,out] as is
+    DevBuf w4, w5;         // [25][128 in][128 out]  = TF [kh,kw,out,in] transposed per tap
+    DevBuf w6m;            // [128 in][128]  column ky*9+kx of weights_6 (columns >= 81 are zero)
+    DevBuf gamma[6], beta[6], bias[5];
+    // K-major copies (hi / lo tf32 split) for the tcgen05 path: [tap][128 out][Cin]
+    DevBuf wk_hi[6], wk_lo[6], gk_hi[6], gk_lo[6];
+
+    // ---- transform workspace for `ws_n` images of ws_h x ws_w ----
+    uint32_t ws_n = 0, ws_h = 0, ws_w = 0;
+    DevBuf bufA, buf1, buf2, buf3, img_u8, rec_u8;
+
+    // ---- coder workspace ----
+    uint32_t cw_streams = 0, cw_size = 0, cw_L = 0, cw_slot = 0;
+    DevBuf idx_planar, bac_slots, byp_slots, bac_bits, byp_bits, err, bac_off, byp_off, total_bytes;
+    DevBuf table, mean, delta, flag, stats;
+    uint64_t last_idx_elems = 0;
+};
+
+namespace {
+
+constexpr uint32_t kHeaderBytes = 32;
+constexpr uint32_t kMagic = 0x42454145u;  // 'EAEB' little-endian
+constexpr uint32_t kVersion = 1;
+
+// Images per internal chunk: keeps the fp32 activation workspace (about 29 MB per 512x768 image)
+// within a few GB regardless of the batch the caller passes.
+uint32_t chunk_images(uint32_t h, uint32_t w)
+{
+    const uint64_t per_image = (uint64_t)(h / 4) * (w / 4) * 128 * 4 * 2 + (uint64_t)(h / 8) * (w / 8) * 128 * 4 +
+                               (uint64_t)(h / 16) * (w / 16) * 128 * 4;
+    uint64_t n = (6ull << 30) / per_image;
+    if (n < 1) n = 1;
+    if (n > 256) n = 256;
+    return (uint32_t)n;
+}
+
+int upload(DevBuf& d, const float* host, size_t n)
+{
+    EAE_TRY(d.alloc(n * sizeof(float)));
+    EAE_CUDA_OK(cudaMemcpy(d.p, host, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// tf32 split used by the 3xTF32 mode: hi = round-to-nearest-even to 10 mantissa bits, lo = x - hi
+// (exact in fp32), then lo rounded the same way.
+float tf32_round(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u += 0x00000FFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& v)
+{
+    std::vector<float> h(v.size()), l(v.size());
+    for (size_t i = 0; i < v.size(); i++) { h[i] = tf32_round(v[i]); l[i] = tf32_round(v[i] - h[i]); }
+    EAE_TRY(upload(hi, h.data(), h.size()));
+    EAE_TRY(upload(lo, l.data(), l.size()));
+    return 0;
+}
+
+int ensure_workspace(eae_codec* c, uint32_t n, uint32_t h, uint32_t w)
+{
+    if (c->ws_n >= n && c->ws_h == h && c->ws_w == w) return 0;
+    const size_t p1 = (size_t)(h / 4) * (w / 4), p2 = (size_t)(h / 8) * (w / 8), p3 = (size_t)(h / 16) * (w / 16);
+    EAE_TRY(c->bufA.alloc(n * p1 * 128 * 4));
+    EAE_TRY(c->buf1.alloc(n * p1 * 128 * 4));
+    EAE_TRY(c->buf2.alloc(n * p2 * 128 * 4));
+    EAE_TRY(c->buf3.alloc(n * p3 * 128 * 4));
+    c->ws_n = n; c->ws_h = h; c->ws_w = w;
+    return 0;
+}
+
+int ensure_coder(eae_codec* c, uint32_t n_streams, uint32_t size, uint32_t L)
+{
+    const uint32_t slot = eae_coder_slot_bytes(size, L);
+    if (c->cw_streams >= n_streams && c->cw_size == size && c->cw_L == L) return 0;
+    EAE_TRY(c->idx_planar.alloc((size_t)n_streams * size * 2));
+    EAE_TRY(c->bac_slots.alloc((size_t)n_streams * slot));
+    EAE_TRY(c->byp_slots.alloc((size_t)n_streams * slot));
+    EAE_TRY(c->bac_bits.alloc((size_t)n_streams * 4));
+    EAE_TRY(c->byp_bits.alloc((size_t)n_streams * 4));
+    EAE_TRY(c->err.alloc((size_t)n_streams * 4));
+    EAE_TRY(c->bac_off.alloc((size_t)n_streams * 8));
+    EAE_TRY(c->byp_off.alloc((size_t)n_streams * 8));
+    if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
+    if (!c->flag.p) EAE_TRY(c->flag.alloc(8));   // [0] bit flags, [1] first coder error
+    if (!c->stats.p) EAE_TRY(c->stats.alloc(sizeof(eae_batch_stats_t)));
+    c->cw_streams = n_streams; c->cw_size = size; c->cw_L = L; c->cw_slot = slot;
+    return 0;
+}
+
+int upload_params(eae_codec* c, const eae_coding_params_t* prm, cudaStream_t st)
+{
+    if (!prm || !prm->bin_widths || !prm->table) { set_error("coding params: NULL pointer"); return EAE_ERR_NULL; }
+    const uint32_t L = prm->truncated_unary_length;
+    if (L == 0) { set_error("truncated unary length is 0"); return EAE_ERR_UNARY_LENGTH; }
+    if (L > 255) { set_error("truncated unary length %u exceeds 255", L); return EAE_ERR_ARGUMENT; }
+    for (int i = 0; i < EAE_NB_MAPS; i++)
+        if (!(prm->bin_widths[i] > 0.f)) { set_error("A quantization bin width is not strictly positive."); return EAE_ERR_ARGUMENT; }
+    if (c->table.bytes < (size_t)EAE_NB_MAPS * L * 8) EAE_TRY(c->table.alloc((size_t)EAE_NB_MAPS * L * 8));
+    if (!c->mean.p) EAE_TRY(c->mean.alloc(EAE_NB_MAPS * 4));
+    if (!c->delta.p) EAE_TRY(c->delta.alloc(EAE_NB_MAPS * 4));
+    EAE_CUDA_OK(cudaMemcpyAsync(c->table.p, prm->table, (size_t)EAE_NB_MAPS * L * 8, cudaMemcpyHostToDevice, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(c->delta.p, prm->bin_widths, EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
+    if (prm->map_mean) EAE_CUDA_OK(cudaMemcpyAsync(c->mean.p, prm->map_mean, EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
+    else EAE_CUDA_OK(cudaMemsetAsync(c->mean.p, 0, EAE_NB_MAPS * 4, st));
+    return 0;
+}
+
+int check_dims(uint32_t n, uint32_t h, uint32_t w)
+{
+    // EntropyAutoencoder.py:77-80, IsolatedDecoder.py:50-53
+    if (h == 0 || w == 0 || h % EAE_STRIDE_PROD != 0 || w % EAE_STRIDE_PROD != 0) {
+        set_error("The height/width of the images (%u x %u) is not divisible by the product of the three strides.", h, w);
+        return EAE_ERR_ARGUMENT;
+    }
+    if ((uint64_t)n * (h / 4) * (w / 4) >= (1ull << 31)) { set_error("batch too large"); return EAE_ERR_ARGUMENT; }
+    return 0;
+}
+
+// ---- layer launchers --------------------------------------------------------------------------
+int run_gemm(eae_codec* c, const GemmPlan& plan, int layer_for_umma, cudaStream_t st)
+{
+    if (c->math == EAE_MATH_FP32_SIMT || layer_for_umma < 0) return launch_gemm_simt(plan, st);
+    (void)layer_for_umma;
+    return launch_gemm_umma(plan, nullptr, c->math == EAE_MATH_TF32X3, st);
+}
+
+GemmPlan base_plan(const float* in, int Hin, int Win, int Cin, const float* w, const float* bias, float* out,
+                   uint32_t n)
+{
+    GemmPlan p;
+    memset(&p, 0, sizeof p);
+    p.in = in; p.w = w; p.bias = bias; p.out = out;
+    p.Hin = Hin; p.Win = Win; p.Cin = Cin;
+    p.Hg = Hin; p.Wg = Win; p.in_mul = 1;
+    p.Hout = Hin; p.Wout = Win; p.out_mul = 1; p.out_r = 0; p.out_s = 0;
+    p.mode = kEpiBias; p.n_taps = 1;
+    p.taps[0] = Tap{0, 0, 0};
+    p.M = n * (uint32_t)Hin * (uint32_t)Win;
+    return p;
+}
+
+// GDN / IGDN as a 1-tap contraction with the squared input (tfutils.py:393-397, 506-509).
+int run_gdn(eae_codec* c, const float* in, float* out, int H, int W, uint32_t n, int which, bool inverse,
+            cudaStream_t st)
+{
+    GemmPlan p = base_plan(in, H, W, 128, c->gamma[which].as<float>(), c->beta[which].as<float>(), out, n);
+    p.mode = inverse ? kEpiIgdn : kEpiGdn;
+    return run_gemm(c, p, -1, st);
+}
+
+// conv k5 s2 SAME: out grid = in / 2, taps (ky - 1, kx - 1) (TF pads 1 before, 2 after).
+int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, const float* bias,
+                float* out, uint32_t n, cudaStream_t st)
+{
+    GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
+    p.Hg = Hin / 2; p.Wg = Win / 2; p.in_mul = 2;
+    p.Hout = p.Hg; p.Wout = p.Wg;
+    p.n_taps = 25;
+    for (int ky = 0; ky < 5; ky++)
+        for (int kx = 0; kx < 5; kx++)
+            p.taps[ky * 5 + kx] = Tap{ky - 1, kx - 1, (uint32_t)(ky * 5 + kx) * 128u * 128u};
+    p.M = n * (uint32_t)p.Hg * (uint32_t)p.Wg;
+    return run_gemm(c, p, 0, st);
+}
+
+// conv2d_transpose k5 s2 SAME = 4 output phases; out[2a + r] gathers in[a + dy] through ky = r + 1 - 2 dy.
+int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, const float* bias,
+                 float* out, uint32_t n, cudaStream_t st)
+{
+    for (int r = 0; r < 2; r++) {
+        for (int s = 0; s < 2; s++) {
+            GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
+            p.Hout = 2 * Hin; p.Wout = 2 * Win; p.out_mul = 2; p.out_r = r; p.out_s = s;
+            int nt = 0;
+            for (int ky = 0; ky < 5; ky++) {
+                if (((r + 1 - ky) & 1) != 0) continue;
+                const int dy = (r + 1 - ky) / 2;
+                for (int kx = 0; kx < 5; kx++) {
+                    if (((s + 1 - kx) & 1) != 0) continue;
+                    const int dx = (s + 1 - kx) / 2;
+                    p.taps[nt++] = Tap{dy, dx, (uint32_t)(ky * 5 + kx) * 128u * 128u};
+                }
+            }
+            p.n_taps = nt;
+            EAE_TRY(run_gemm(c, p, 0, st));
+        }
+    }
+    return 0;
+}
+
+int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, uint32_t w, float* y_dev,
+                 cudaStream_t st)
+{
+    const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8, H3 = h / 16, W3 = w / 16;
+    float* A = c->bufA.as<float>();
+    float* x1 = c->buf1.as<float>();
+    float* x2 = c->buf2.as<float>();
+    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction, then GDN
+    EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st));
+    {
+        GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
+        EAE_TRY(run_gemm(c, p, -1, st));
+    }
+    EAE_TRY(run_gdn(c, x1, x1, H1, W1, n, 0, false, st));
+    // layer 2
+    EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), c->bias[1].as<float>(), x2, n, st));
+    EAE_TRY(run_gdn(c, x2, x2, H2, W2, n, 1, false, st));
+    // layer 3
+    EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), c->bias[2].as<float>(), y_dev, n, st));
+    if (!c->learned) EAE_TRY(run_gdn(c, y_dev, y_dev, H3, W3, n, 2, false, st));
+    return 0;
+}
+
+int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint32_t w, uint8_t* out_u8_dev,
+                 float* out_f32_dev, cudaStream_t st)
+{
+    const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8, H3 = h / 16, W3 = w / 16;
+    float* P = c->bufA.as<float>();
+    float* x1 = c->buf1.as<float>();
+    float* x2 = c->buf2.as<float>();
+    float* x3 = c->buf3.as<float>();
+    const float* src = q_dev;
+    if (!c->learned) {
+        EAE_TRY(run_gdn(c, q_dev, x3, H3, W3, n, 3, true, st));
+        src = x3;
+    }
+    EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), c->bias[3].as<float>(), x2, n, st));
+    EAE_TRY(run_gdn(c, x2, x2, H2, W2, n, 4, true, st));
+    EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), c->bias[4].as<float>(), x1, n, st));
+    EAE_TRY(run_gdn(c, x1, x1, H1, W1, n, 5, true, st));
+    // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias: per-pixel tap contributions, then col2im
+    {
+        GemmPlan p = base_plan(x1, H1, W1, 128, c->w6m.as<float>(), nullptr, P, n);
+        EAE_TRY(run_gemm(c, p, -1, st));
+    }
+    EAE_TRY(launch_col2im_k9s4(P, out_u8_dev, out_f32_dev, n, (int)h, (int)w, st));
+    return 0;
+}
+
+// ---- container kernels -------------------------------------------------------------------------
+// Exclusive scan of per-stream byte sizes -> payload offsets. Single CTA, 1024 threads.
+__global__ void __launch_bounds__(1024)
+stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
+                      uint32_t bits_stride, uint32_t n, uint64_t base, uint64_t* __restrict__ bac_off,
+                      uint64_t* __restrict__ byp_off, uint64_t* __restrict__ total_out)
+{
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t running;
+    if (threadIdx.x == 0) running = base;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t start = 0; start < n; start += 1024) {
+        const uint32_t s = start + threadIdx.x;
+        uint64_t nb = 0, nr = 0;
+        if (s < n) {
+            nb = (bac_bits[(size_t)s * bits_stride] + 7u) >> 3;
+            nr = (byp_bits[(size_t)s * bits_stride] + 7u) >> 3;
+        }
+        uint64_t v = nb + nr;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_sum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t ws = warp_sum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const uint64_t incl = v + (wid ? warp_sum[wid - 1] : 0);
+        const uint64_t at = running + incl - (nb + nr);
+        if (s < n) { bac_off[s] = at; byp_off[s] = at + nb; }
+        __syncthreads();
+        if (threadIdx.x == 1023) running += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = running;
+}
+
+__global__ void write_header_kernel(uint8_t* __restrict__ container, uint32_t n, uint32_t h, uint32_t w,
+                                    uint32_t L, const uint32_t* __restrict__ bac_bits,
+                                    const uint32_t* __restrict__ byp_bits, uint32_t n_streams)
+{
+    uint32_t* c32 = reinterpret_cast<uint32_t*>(container);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {
+        c32[0] = kMagic; c32[1] = kVersion; c32[2] = n; c32[3] = h; c32[4] = w; c32[5] = EAE_NB_MAPS; c32[6] = L; c32[7] = 0;
+    }
+    if (s < n_streams) {
+        c32[8 + 2 * (size_t)s] = bac_bits[s];
+        c32[8 + 2 * (size_t)s + 1] = byp_bits[s];
+    }
+}
+
+// One warp per stream: slot bytes -> payload (destination byte-aligned only).
+__global__ void __launch_bounds__(256)
+pack_payload_kernel(uint8_t* __restrict__ container, uint64_t cap, const uint8_t* __restrict__ bac_slots,
+                    const uint8_t* __restrict__ byp_slots, uint32_t slot_bytes,
+                    const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
+                    const uint64_t* __restrict__ bac_off, const uint64_t* __restrict__ byp_off, uint32_t n_streams)
+{
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_streams) return;
+    const uint32_t nb = (bac_bits[s] + 7u) >> 3, nr = (byp_bits[s] + 7u) >> 3;
+    const uint64_t ob = bac_off[s], orr = byp_off[s];
+    if (orr + nr > cap) return;   // host checks total_bytes against the capacity
+    const uint8_t* sb = bac_slots + (size_t)s * slot_bytes;
+    const uint8_t* sr = byp_slots + (size_t)s * slot_bytes;
+    for (uint32_t i = lane; i < nb; i += 32) container[ob + i] = sb[i];
+    for (uint32_t i = lane; i < nr; i += 32) container[orr + i] = sr[i];
+}
+
+__global__ void batch_stats_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
+                                   const uint32_t* __restrict__ err, uint32_t n_streams,
+                                   eae_batch_stats_t* __restrict__ stats, uint32_t* __restrict__ flag)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const unsigned long long bits = (unsigned long long)bac_bits[s] + byp_bits[s];
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bits_per_map[s % EAE_NB_MAPS]), bits);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->total_bits), bits);
+    // A map is dead (tools.py:294-320) iff all its symbols are 0 iff no sign bit was written.
+    if (byp_bits[s] == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->nb_dead_maps), 1ull);
+    if (err[s]) atomicCAS(flag + 1, 0u, err[s]);   // first stream error wins
+}
+
+int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* img_dev, uint32_t n,
+                      uint32_t h, uint32_t w, uint8_t* container_dev, uint64_t cap, uint64_t* total_dev,
+                      eae_batch_stats_t* stats_dev, cudaStream_t st)
+{
+    EAE_TRY(check_dims(n, h, w));
+    EAE_TRY(upload_params(c, prm, st));
+    const uint32_t L = prm->truncated_unary_length;
+    const uint32_t hw3 = (h / 16) * (w / 16);
+    const uint32_t n_streams = n * EAE_NB_MAPS;
+    const uint32_t chunk = chunk_images(h, w);
+    EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
+    EAE_TRY(ensure_coder(c, n_streams, hw3, L));
+    if (cap < kHeaderBytes + 8ull * n_streams) { set_error("container capacity too small"); return EAE_ERR_ARGUMENT; }
+    EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
+    for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
+        float* y = c->buf3.as<float>();
+        EAE_TRY(encode_chunk(c, img_dev + (size_t)i0 * h * w, nc, h, w, y, st));
+        EAE_TRY(launch_quantize_to_planar(y, c->mean.as<float>(), c->delta.as<float>(),
+                                          c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3, nullptr,
+                                          nc, hw3, c->flag.as<uint32_t>(), st));
+    }
+    c->last_idx_elems = (uint64_t)n_streams * hw3;
+    EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
+                                  nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
+                                  c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st));
+    stream_offsets_kernel<<<1, 1024, 0, st>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
+                                              kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
+                                              c->byp_off.as<uint64_t>(), total_dev);
+    EAE_LAUNCH_OK();
+    write_header_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(container_dev, n, h, w, L,
+                                                                     c->bac_bits.as<uint32_t>(),
+                                                                     c->byp_bits.as<uint32_t>(), n_streams);
+    EAE_LAUNCH_OK();
+    pack_payload_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, st>>>(
+        container_dev, cap, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
+        c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->bac_off.as<uint64_t>(),
+        c->byp_off.as<uint64_t>(), n_streams);
+    EAE_LAUNCH_OK();
+    eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
+    EAE_CUDA_OK(cudaMemsetAsync(sd, 0, sizeof(eae_batch_stats_t), st));
+    batch_stats_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(c->bac_bits.as<uint32_t>(),
+                                                                    c->byp_bits.as<uint32_t>(),
+                                                                    c->err.as<uint32_t>(), n_streams, sd,
+                                                                    c->flag.as<uint32_t>());
+    EAE_LAUNCH_OK();
+    return 0;
+}
+
+int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* container_dev, uint32_t n,
+                        uint32_t h, uint32_t w, uint8_t* rec_dev, cudaStream_t st)
+{
+    EAE_TRY(check_dims(n, h, w));
+    EAE_TRY(upload_params(c, prm, st));
+    const uint32_t L = prm->truncated_unary_length;
+    const uint32_t hw3 = (h / 16) * (w / 16);
+    const uint32_t n_streams = n * EAE_NB_MAPS;
+    const uint32_t chunk = chunk_images(h, w);
+    EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
+    EAE_TRY(ensure_coder(c, n_streams, hw3, L));
+    EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
+    const uint32_t* tbl = reinterpret_cast<const uint32_t*>(container_dev + kHeaderBytes);
+    stream_offsets_kernel<<<1, 1024, 0, st>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
+                                              c->bac_off.as<uint64_t>(), c->byp_off.as<uint64_t>(),
+                                              c->total_bytes.as<uint64_t>());
+    EAE_LAUNCH_OK();
+    // De-interleave the stream table into the bit-count arrays the decoder reads.
+    EAE_CUDA_OK(cudaMemcpy2DAsync(c->bac_bits.p, 4, tbl, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
+    EAE_CUDA_OK(cudaMemcpy2DAsync(c->byp_bits.p, 4, tbl + 1, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
+    EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
+                                  nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
+                                  container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
+                                  c->err.as<uint32_t>(), st));
+    c->last_idx_elems = (uint64_t)n_streams * hw3;
+    for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
+        // the dequantized latent lives in bufA's tail-free region: use buf3 when IGDN4 is absent,
+        // otherwise a separate buffer is needed because IGDN4 writes buf3.
+        float* q = c->learned ? c->buf3.as<float>() : c->bufA.as<float>();
+        EAE_TRY(launch_dequantize_from_planar(c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3,
+                                              c->mean.as<float>(), c->delta.as<float>(), q, nc, hw3, st));
+        EAE_TRY(decode_chunk(c, q, nc, h, w, rec_dev + (size_t)i0 * h * w, nullptr, st));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int learned, int device)
+{
+    if (!out || !wt) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    const float* need[] = {wt->weights_1, wt->biases_1, wt->gamma_1, wt->beta_1, wt->weights_2, wt->biases_2,
+                           wt->gamma_2, wt->beta_2, wt->weights_3, wt->biases_3, wt->weights_4, wt->biases_4,
+                           wt->gamma_5, wt->beta_5, wt->weights_5, wt->biases_5, wt->gamma_6, wt->beta_6,
+                           wt->weights_6};
+    for (const float* p : need) if (!p) { set_error("a required weight pointer is NULL"); return EAE_ERR_NULL; }
+    if (!learned && (!wt->gamma_3 || !wt->beta_3 || !wt->gamma_4 || !wt->beta_4)) {
+        set_error("gamma_3/beta_3/gamma_4/beta_4 are required when the bin widths are not learned");
+        return EAE_ERR_NULL;
+    }
+    EAE_TRY(require_device());
+    EAE_CUDA_OK(cudaSetDevice(device));
+    std::unique_ptr<eae_codec> c(new eae_codec);
+    c->device = device;
+    c->learned = learned ? 1 : 0;
+
+    // weights_1 [9,9,1,128] -> [96][128]
+    {
+        std::vector<float> m((size_t)kIm2colK * 128, 0.f);
+        memcpy(m.data(), wt->weights_1, (size_t)81 * 128 * 4);
+        EAE_TRY(upload(c->w1m, m.data(), m.size()));
+    }
+    EAE_TRY(upload(c->w2, wt->weights_2, (size_t)25 * 128 * 128));
+    EAE_TRY(upload(c->w3, wt->weights_3, (size_t)25 * 128 * 128));
+    // conv2d_transpose filters [kh,kw,out,in] -> per tap [in][out]
+    auto transpose_taps = [](const float* src, std::vector<float>& dst) {
+        dst.resize((size_t)25 * 128 * 128);
+        for (int t = 0; t < 25; t++)
+            for (int o = 0; o < 128; o++)
+                for (int i = 0; i < 128; i++)
+                    dst[((size_t)t * 128 + i) * 128 + o] = src[((size_t)t * 128 + o) * 128 + i];
+    };
+    {
+        std::vector<float> t4, t5;
+        transpose_taps(wt->weights_4, t4);
+        transpose_taps(wt->weights_5, t5);
+        EAE_TRY(upload(c->w4, t4.data(), t4.size()));
+        EAE_TRY(upload(c->w5, t5.data(), t5.size()));
+    }
+    // weights_6 [9,9,1(out),128(in)] -> [128 in][128 cols], column = ky*9+kx
+    {
+        std::vector<float> m((size_t)128 * 128, 0.f);
+        for (int t = 0; t < 81; t++)
+            for (int i = 0; i < 128; i++) m[(size_t)i * 128 + t] = wt->weights_6[(size_t)t * 128 + i];
+        EAE_TRY(upload(c->w6m, m.data(), m.size()));
+    }
+    const float* gammas[6] = {wt->gamma_1, wt->gamma_2, wt->gamma_3, wt->gamma_4, wt->gamma_5, wt->gamma_6};
+    const float* betas[6] = {wt->beta_1, wt->beta_2, wt->beta_3, wt->beta_4, wt->beta_5, wt->beta_6};
+    for (int i = 0; i < 6; i++) {
+        if (!gammas[i]) continue;
+        EAE_TRY(upload(c->gamma[i], gammas[i], (size_t)128 * 128));
+        EAE_TRY(upload(c->beta[i], betas[i], 128));
+    }
+    const float* biases[5] = {wt->biases_1, wt->biases_2, wt->biases_3, wt->biases_4, wt->biases_5};
+    for (int i = 0; i < 5; i++) EAE_TRY(upload(c->bias[i], biases[i], 128));
+    *out = c.release();
+    return 0;
+}
+
+extern "C" int eae_codec_destroy(eae_codec_t* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    delete c;
+    return 0;
+}
+
+extern "C" int eae_codec_set_math(eae_codec_t* c, int mode)
+{
+    if (!c) { set_error("NULL codec"); return EAE_ERR_NULL; }
+    if (mode != EAE_MATH_FP32_SIMT && mode != EAE_MATH_TF32X3 && mode != EAE_MATH_TF32) {
+        set_error("unknown math mode %d", mode); return EAE_ERR_ARGUMENT;
+    }
+    if (mode != EAE_MATH_FP32_SIMT) EAE_TRY(umma_available());
+    c->math = mode;
+    return 0;
+}
+
+extern "C" int eae_codec_get_math(const eae_codec_t* c) { return c ? c->math : EAE_ERR_NULL; }
+
+extern "C" int eae_encode_dev(eae_codec_t* c, const uint8_t* img_dev, uint32_t n, uint32_t h, uint32_t w,
+                              float* y_dev, void* stream)
+{
+    if (!c || !img_dev || !y_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t chunk = chunk_images(h, w);
+    EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
+    const size_t ypi = (size_t)(h / 16) * (w / 16) * 128;
+    for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
+        EAE_TRY(encode_chunk(c, img_dev + (size_t)i0 * h * w, nc, h, w, y_dev + i0 * ypi, st));
+    }
+    return 0;
+}
+
+extern "C" int eae_decode_dev(eae_codec_t* c, const float* q_dev, uint32_t n, uint32_t h, uint32_t w,
+                              uint8_t* rec_dev, void* stream)
+{
+    if (!c || !q_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t chunk = chunk_images(h, w);
+    EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
+    const size_t ypi = (size_t)(h / 16) * (w / 16) * 128;
+    for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
+        EAE_TRY(decode_chunk(c, q_dev + i0 * ypi, nc, h, w, rec_dev + (size_t)i0 * h * w, nullptr, st));
+    }
+    return 0;
+}
+
+extern "C" int eae_encode_host(eae_codec_t* c, const uint8_t* img, uint32_t n, uint32_t h, uint32_t w,
+                               float* y_out, void* stream)
+{
+    if (!c || !img || !y_out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf di, dy;
+    const size_t nin = (size_t)n * h * w, ny = (size_t)n * (h / 16) * (w / 16) * 128;
+    EAE_TRY(di.alloc(nin));
+    EAE_TRY(dy.alloc(ny * 4));
+    EAE_CUDA_OK(cudaMemcpyAsync(di.p, img, nin, cudaMemcpyHostToDevice, st));
+    EAE_TRY(eae_encode_dev(c, di.as<uint8_t>(), n, h, w, dy.as<float>(), stream));
+    EAE_CUDA_OK(cudaMemcpyAsync(y_out, dy.p, ny * 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int eae_decode_host(eae_codec_t* c, const float* q, uint32_t n, uint32_t h, uint32_t w,
+                               uint8_t* rec_out, void* stream)
+{
+    if (!c || !q || !rec_out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf dq, dr;
+    const size_t nout = (size_t)n * h * w, nq = (size_t)n * (h / 16) * (w / 16) * 128;
+    EAE_TRY(dq.alloc(nq * 4));
+    EAE_TRY(dr.alloc(nout));
+    EAE_CUDA_OK(cudaMemcpyAsync(dq.p, q, nq * 4, cudaMemcpyHostToDevice, st));
+    EAE_TRY(eae_decode_dev(c, dq.as<float>(), n, h, w, dr.as<uint8_t>(), stream));
+    EAE_CUDA_OK(cudaMemcpyAsync(rec_out, dr.p, nout, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" uint64_t eae_container_bound(uint32_t n, uint32_t h, uint32_t w, uint32_t L)
+{
+    const uint64_t size = (uint64_t)(h / 16) * (w / 16);
+    const uint64_t n_streams = (uint64_t)n * EAE_NB_MAPS;
+    return kHeaderBytes + 8 * n_streams + 2 * n_streams * (uint64_t)eae_coder_capacity_bytes((uint32_t)size, L);
+}
+
+extern "C" int eae_compress_dev(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* img_dev,
+                                uint32_t n, uint32_t h, uint32_t w, uint8_t* container_dev, uint64_t cap,
+                                uint64_t* total_dev, eae_batch_stats_t* stats_dev, void* stream)
+{
+    if (!c || !img_dev || !container_dev || !total_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    return compress_dev_impl(c, prm, img_dev, n, h, w, container_dev, cap, total_dev, stats_dev,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int eae_decompress_dev(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* container_dev,
+                                  uint32_t n, uint32_t h, uint32_t w, uint8_t* rec_dev, void* stream)
+{
+    if (!c || !container_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    return decompress_dev_impl(c, prm, container_dev, n, h, w, rec_dev, (cudaStream_t)stream);
+}
+
+extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* img, uint32_t n,
+                                 uint32_t h, uint32_t w, uint8_t* container, uint64_t cap, uint64_t* out_bytes,
+                                 eae_batch_stats_t* stats, void* stream)
+{
+    if (!c || !img || !container || !out_bytes) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nin = (size_t)n * h * w;
+    if (c->img_u8.bytes < nin) EAE_TRY(c->img_u8.alloc(nin));
+    // Device-side container: sized by the bytes actually produced is unknown before coding, so the
+    // staging buffer is sized by the caller's capacity (bounded by the worst case).
+    uint64_t bound = eae_container_bound(n, h, w, prm ? prm->truncated_unary_length : 1);
+    uint64_t dcap = cap < bound ? cap : bound;
+    if (c->rec_u8.bytes < dcap) EAE_TRY(c->rec_u8.alloc(dcap));
+    EAE_CUDA_OK(cudaMemcpyAsync(c->img_u8.p, img, nin, cudaMemcpyHostToDevice, st));
+    if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
+    EAE_TRY(compress_dev_impl(c, prm, c->img_u8.as<uint8_t>(), n, h, w, c->rec_u8.as<uint8_t>(), dcap,
+                              c->total_bytes.as<uint64_t>(), nullptr, st));
+    uint64_t total = 0;
+    uint32_t flag[2] = {0, 0};
+    eae_batch_stats_t hs;
+    EAE_CUDA_OK(cudaMemcpyAsync(&total, c->total_bytes.p, 8, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(flag, c->flag.p, 8, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(&hs, c->stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (flag[0] & 1u) { set_error("The rounded array elements cannot be represented as 16-bit signed integers."); return EAE_ERR_INT16_RANGE; }
+    if (flag[1]) { set_error("Error of type %u during the encoding.", flag[1]); return (int)flag[1]; }
+    if (total > dcap) { set_error("container needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)cap); return EAE_ERR_ARGUMENT; }
+    EAE_CUDA_OK(cudaMemcpyAsync(container, c->rec_u8.p, total, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    *out_bytes = total;
+    if (stats) *stats = hs;
+    return 0;
+}
+
+extern "C" int eae_decompress_host(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* container,
+                                   uint64_t nbytes, uint8_t* rec, uint64_t rec_cap, void* stream)
+{
+    if (!c || !container || !rec) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (nbytes < kHeaderBytes) { set_error("container shorter than its header"); return EAE_ERR_ARGUMENT; }
+    uint32_t hdr[8];
+    memcpy(hdr, container, sizeof hdr);
+    if (hdr[0] != kMagic || hdr[1] != kVersion || hdr[5] != EAE_NB_MAPS) { set_error("not an EAEB v1 container"); return EAE_ERR_ARGUMENT; }
+    const uint32_t n = hdr[2], h = hdr[3], w = hdr[4];
+    EAE_TRY(check_dims(n, h, w));
+    if (prm && prm->truncated_unary_length != hdr[6]) { set_error("container was coded with L = %u", hdr[6]); return EAE_ERR_ARGUMENT; }
+    const uint64_t n_streams = (uint64_t)n * EAE_NB_MAPS;
+    if (nbytes < kHeaderBytes + 8 * n_streams) { set_error("container shorter than its stream table"); return EAE_ERR_ARGUMENT; }
+    // Validate the payload size on the host before trusting offsets on the device.
+    uint64_t need = kHeaderBytes + 8 * n_streams;
+    const uint32_t cap_bits = eae_coder_capacity_bytes((h / 16) * (w / 16), hdr[6]) * 8;
+    for (uint64_t s = 0; s < n_streams; s++) {
+        uint32_t bb, rb;
+        memcpy(&bb, container + kHeaderBytes + 8 * s, 4);
+        memcpy(&rb, container + kHeaderBytes + 8 * s + 4, 4);
+        if (bb > cap_bits || rb > cap_bits) { set_error("stream %llu exceeds the coder capacity", (unsigned long long)s); return EAE_ERR_CAPACITY; }
+        need += ((uint64_t)bb + 7) / 8 + ((uint64_t)rb + 7) / 8;
+    }
+    if (need > nbytes) { set_error("container truncated: needs %llu bytes", (unsigned long long)need); return EAE_ERR_RESOURCE; }
+    if ((uint64_t)n * h * w > rec_cap) { set_error("reconstruction buffer too small"); return EAE_ERR_ARGUMENT; }
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->rec_u8.bytes < nbytes + 16) EAE_TRY(c->rec_u8.alloc(nbytes + 16));
+    const size_t nout = (size_t)n * h * w;
+    if (c->img_u8.bytes < nout) EAE_TRY(c->img_u8.alloc(nout));
+    EAE_CUDA_OK(cudaMemcpyAsync(c->rec_u8.p, container, nbytes, cudaMemcpyHostToDevice, st));
+    EAE_TRY(decompress_dev_impl(c, prm, c->rec_u8.as<uint8_t>(), n, h, w, c->img_u8.as<uint8_t>(), st));
+    std::vector<uint32_t> herr(n_streams);
+    EAE_CUDA_OK(cudaMemcpyAsync(herr.data(), c->err.p, n_streams * 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(rec, c->img_u8.p, nout, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    for (uint64_t s = 0; s < n_streams; s++)
+        if (herr[s]) { set_error("Error of type %u during the decoding.", herr[s]); return (int)herr[s]; }
+    return 0;
+}
+
+extern "C" int eae_last_indices_host(eae_codec_t* c, int16_t* out, uint64_t n_elems)
+{
+    if (!c || !out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (n_elems > c->last_idx_elems) { set_error("only %llu indices available", (unsigned long long)c->last_idx_elems); return EAE_ERR_ARGUMENT; }
+    EAE_CUDA_OK(cudaMemcpy(out, c->idx_planar.p, n_elems * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}

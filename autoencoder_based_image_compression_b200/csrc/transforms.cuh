@@ -1,0 +1,27 @@
+// Launchers of the transform kernels (transforms_simt.cu, conv_umma.cu), internal to the library.
+#pragma once
+
+#include "common.cuh"
+#include "conv_plan.cuh"
+
+namespace eae {
+
+constexpr int kIm2colK = 96;  // 81 taps of the 9x9 kernel, zero-padded to a multiple of 32
+
+// fp32 FFMA tap-list GEMM (always available).
+int launch_gemm_simt(const GemmPlan& plan, cudaStream_t st);
+// tcgen05 / TMEM / TMA tap-list GEMM; exact3x = hi/lo split of both operands (3 MMAs per product).
+// w_lo: the low parts of the weights, same layout as plan.w (only read when exact3x).
+int launch_gemm_umma(const GemmPlan& plan, const float* w_lo, bool exact3x, cudaStream_t st);
+// 0 if the tcgen05 path can run on the current device (sm_100), else an error code with message.
+int umma_available();
+
+int launch_im2col_k9s4(const uint8_t* img, float* out, uint32_t n, int H, int W, cudaStream_t st);
+int launch_col2im_k9s4(const float* P, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
+                       cudaStream_t st);
+int launch_quantize_to_planar(const float* y, const float* mean, const float* delta, int16_t* idx_planar,
+                              float* q_off, uint32_t n, uint32_t hw, uint32_t* flag, cudaStream_t st);
+int launch_dequantize_from_planar(const int16_t* idx_planar, const float* mean, const float* delta,
+                                  float* q_off, uint32_t n, uint32_t hw, cudaStream_t st);
+
+}  // namespace eae
