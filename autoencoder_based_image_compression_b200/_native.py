@@ -61,6 +61,11 @@ PROTOTYPES = {
     'eae_device_count': (c_int, []),
     'eae_device_info': (c_int, [c_int, P(c_int), P(c_int), P(c_int), P(ctypes.c_size_t)]),
     'eae_launch_count': (u64, []),
+    'eae_set_device': (c_int, [c_int]),
+    'eae_profile_enable': (c_int, [c_int]),
+    'eae_profile_reset': (c_int, []),
+    'eae_profile_read': (c_int, [c_int, P(u64), P(ctypes.c_double)]),
+    'eae_profile_name': (ctypes.c_char_p, [c_int]),
     'eae_host_alloc': (c_void_p, [ctypes.c_size_t]),
     'eae_host_free': (None, [c_void_p]),
     'eae_device_alloc': (c_void_p, [ctypes.c_size_t]),

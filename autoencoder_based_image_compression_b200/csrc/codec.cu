@@ -149,6 +149,8 @@ int check_dims(uint32_t n, uint32_t h, uint32_t w)
 // ---- layer launchers --------------------------------------------------------------------------
 int run_gemm(eae_codec* c, const GemmPlan& plan, int layer_for_umma, cudaStream_t st)
 {
+    ProfScope prof(plan.mode != kEpiBias ? kProfGemmGdn
+                   : (plan.n_taps == 1 ? kProfGemmThin : (plan.out_mul == 2 ? kProfGemmTconv : kProfGemmConv)), st);
     if (c->math == EAE_MATH_FP32_SIMT || layer_for_umma < 0) return launch_gemm_simt(plan, st);
     (void)layer_for_umma;
     return launch_gemm_umma(plan, nullptr, c->math == EAE_MATH_TF32X3, st);
@@ -226,7 +228,7 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
     // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction, then GDN
-    EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st));
+    { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
     {
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
         EAE_TRY(run_gemm(c, p, -1, st));
@@ -263,7 +265,7 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
         GemmPlan p = base_plan(x1, H1, W1, 128, c->w6m.as<float>(), nullptr, P, n);
         EAE_TRY(run_gemm(c, p, -1, st));
     }
-    EAE_TRY(launch_col2im_k9s4(P, out_u8_dev, out_f32_dev, n, (int)h, (int)w, st));
+    { ProfScope prof(kProfCol2im, st); EAE_TRY(launch_col2im_k9s4(P, out_u8_dev, out_f32_dev, n, (int)h, (int)w, st)); }
     return 0;
 }
 
@@ -378,14 +380,19 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
         const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
         float* y = c->buf3.as<float>();
         EAE_TRY(encode_chunk(c, img_dev + (size_t)i0 * h * w, nc, h, w, y, st));
+        ProfScope prof(kProfQuantize, st);
         EAE_TRY(launch_quantize_to_planar(y, c->mean.as<float>(), c->delta.as<float>(),
                                           c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3, nullptr,
                                           nc, hw3, c->flag.as<uint32_t>(), st));
     }
     c->last_idx_elems = (uint64_t)n_streams * hw3;
-    EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
-                                  nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
-                                  c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st));
+    {
+        ProfScope prof(kProfCoderEncode, st);
+        EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
+                                      nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
+                                      c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st));
+    }
+    ProfScope prof_pack(kProfPack, st);
     stream_offsets_kernel<<<1, 1024, 0, st>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
                                               kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
                                               c->byp_off.as<uint64_t>(), total_dev);
@@ -429,18 +436,24 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     // De-interleave the stream table into the bit-count arrays the decoder reads.
     EAE_CUDA_OK(cudaMemcpy2DAsync(c->bac_bits.p, 4, tbl, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
     EAE_CUDA_OK(cudaMemcpy2DAsync(c->byp_bits.p, 4, tbl + 1, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
-    EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
-                                  nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
-                                  container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
-                                  c->err.as<uint32_t>(), st));
+    {
+        ProfScope prof_dec(kProfCoderDecode, st);
+        EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
+                                      nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
+                                      container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
+                                      c->err.as<uint32_t>(), st));
+    }
     c->last_idx_elems = (uint64_t)n_streams * hw3;
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
         const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
         // the dequantized latent lives in bufA's tail-free region: use buf3 when IGDN4 is absent,
         // otherwise a separate buffer is needed because IGDN4 writes buf3.
         float* q = c->learned ? c->buf3.as<float>() : c->bufA.as<float>();
-        EAE_TRY(launch_dequantize_from_planar(c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3,
-                                              c->mean.as<float>(), c->delta.as<float>(), q, nc, hw3, st));
+        {
+            ProfScope prof(kProfDequantize, st);
+            EAE_TRY(launch_dequantize_from_planar(c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3,
+                                                  c->mean.as<float>(), c->delta.as<float>(), q, nc, hw3, st));
+        }
         EAE_TRY(decode_chunk(c, q, nc, h, w, rec_dev + (size_t)i0 * h * w, nullptr, st));
     }
     return 0;
@@ -536,6 +549,7 @@ extern "C" int eae_encode_dev(eae_codec_t* c, const uint8_t* img_dev, uint32_t n
 {
     if (!c || !img_dev || !y_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t chunk = chunk_images(h, w);
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
@@ -552,6 +566,7 @@ extern "C" int eae_decode_dev(eae_codec_t* c, const float* q_dev, uint32_t n, ui
 {
     if (!c || !q_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t chunk = chunk_images(h, w);
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
@@ -611,6 +626,7 @@ extern "C" int eae_compress_dev(eae_codec_t* c, const eae_coding_params_t* prm, 
                                 uint64_t* total_dev, eae_batch_stats_t* stats_dev, void* stream)
 {
     if (!c || !img_dev || !container_dev || !total_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_CUDA_OK(cudaSetDevice(c->device));
     return compress_dev_impl(c, prm, img_dev, n, h, w, container_dev, cap, total_dev, stats_dev,
                              (cudaStream_t)stream);
 }
@@ -619,6 +635,7 @@ extern "C" int eae_decompress_dev(eae_codec_t* c, const eae_coding_params_t* prm
                                   uint32_t n, uint32_t h, uint32_t w, uint8_t* rec_dev, void* stream)
 {
     if (!c || !container_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_CUDA_OK(cudaSetDevice(c->device));
     return decompress_dev_impl(c, prm, container_dev, n, h, w, rec_dev, (cudaStream_t)stream);
 }
 

@@ -65,6 +65,19 @@ struct DevBuf {
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Kernel classes of the optional device-side profile (eae_profile_*).
+enum ProfClass : int {
+    kProfGemmConv = 0, kProfGemmTconv, kProfGemmGdn, kProfGemmThin, kProfIm2col, kProfCol2im, kProfQuantize,
+    kProfDequantize, kProfCoderEncode, kProfCoderDecode, kProfPack, kProfCount
+};
+// Brackets the launches issued during its lifetime with a CUDA event pair when profiling is on.
+struct ProfScope {
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
+
 // Returns 0 if a CUDA device is usable, EAE_ERR_CUDA (with message) otherwise.
 int require_device();
 

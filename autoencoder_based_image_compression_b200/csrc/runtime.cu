@@ -1,6 +1,8 @@
 // Runtime plumbing of libeae_b200.so: last-error text, device checks, pinned/device memory, streams
 // and events for callers (ctypes) that have no CUDA binding of their own.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -34,9 +36,88 @@ int require_device()
     return 0;
 }
 
+// ---- profile ----
+struct ProfEvent { cudaEvent_t a, b; int cls; };
+static std::mutex g_prof_mutex;
+static std::vector<ProfEvent> g_prof_events;
+static std::atomic<int> g_prof_on{0};
+static uint64_t g_prof_launches[kProfCount];
+static double g_prof_ms[kProfCount];
+
+ProfScope::ProfScope(int cls, cudaStream_t st) : slot(-1), stream(st)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfEvent ev;
+    ev.cls = cls;
+    if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) return;
+    cudaEventRecord(ev.a, st);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_events.push_back(ev);
+    slot = (int)g_prof_events.size() - 1;
+}
+
+ProfScope::~ProfScope()
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    cudaEventRecord(g_prof_events[slot].b, stream);
+}
+
+static void prof_drain()
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (ProfEvent& ev : g_prof_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+            g_prof_launches[ev.cls]++;
+            g_prof_ms[ev.cls] += ms;
+        }
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    g_prof_events.clear();
+}
+
 }  // namespace eae
 
 using namespace eae;
+
+extern "C" int eae_set_device(int device)
+{
+    EAE_TRY(require_device());
+    EAE_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int eae_profile_enable(int on)
+{
+    if (!on) prof_drain();
+    g_prof_on.store(on ? 1 : 0);
+    return 0;
+}
+
+extern "C" int eae_profile_reset(void)
+{
+    prof_drain();
+    for (int i = 0; i < kProfCount; i++) { g_prof_launches[i] = 0; g_prof_ms[i] = 0.; }
+    return 0;
+}
+
+extern "C" int eae_profile_read(int cls, uint64_t* launches, double* total_ms)
+{
+    if (cls < 0 || cls >= kProfCount) { set_error("bad kernel class %d", cls); return EAE_ERR_ARGUMENT; }
+    prof_drain();
+    if (launches) *launches = g_prof_launches[cls];
+    if (total_ms) *total_ms = g_prof_ms[cls];
+    return 0;
+}
+
+extern "C" const char* eae_profile_name(int cls)
+{
+    static const char* names[kProfCount] = {"gemm_conv", "gemm_tconv", "gemm_gdn", "gemm_thin", "im2col", "col2im",
+                                            "quantize", "dequantize", "coder_encode", "coder_decode", "pack"};
+    return (cls >= 0 && cls < kProfCount) ? names[cls] : "";
+}
 
 extern "C" const char* eae_last_error(void) { return g_error; }
 

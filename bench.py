@@ -1,0 +1,401 @@
+"""Headline benchmark: images/s of the full EAE codec hot path (encode -> quantize -> lossless code ->
+bitstream -> decode) on synthetic 512 x 768 luminance images.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Under torchrun (N > 1) every rank drives one GPU with its own batch (weak scaling, no data-path
+collective; one NCCL all-reduce of the rate statistics per step). Rank 0 prints ONE JSON line.
+
+A "step" is one pass of the hot path over one batch (BASELINE.json configs[1]: 24 images per GPU):
+  value  images/s with the batch already resident in HBM (eae_compress_dev + eae_decompress_dev)
+  e2e    the same through the public host API (Codec.compress / Codec.decompress) from pinned host
+         memory, host<->device copies inside the timed region
+--impl reference times the CPU implementation (oracle restatement of the transforms on torch-CPU +
+the reference's own C++ coder from oracle/_ref when present, else the C port) on all host cores.
+"""
+import argparse
+import ctypes
+import json
+import multiprocessing
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'images/sec (512x768 luma, encode->bitstream->decode)'
+# algorithmic GFLOP per 512 x 768 image (2 * MACs), fixed-delta variant (6 GDN/IGDN)
+GFLOP_PER_IMAGE = {'gemm_conv': 5.0332 + 1.2583, 'gemm_tconv': 1.2583 + 5.0332,
+                   'gemm_gdn': 2*(0.8053 + 0.2013 + 0.0503), 'gemm_thin': 2*0.5096}
+L2_BYTES = 126 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=24, help='images per GPU per step')
+    ap.add_argument('--height', type=int, default=512)
+    ap.add_argument('--width', type=int, default=768)
+    ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'fp32'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--cpu-sample', type=int, default=0, help='images in the CPU sample (0 = one per core)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def load_tables():
+    with numpy.load(os.path.join(ROOT, 'tests', 'golden', 'tables.npz')) as data:
+        return (numpy.ascontiguousarray(data['1_10000__binary_probabilities_1']),
+                numpy.ascontiguousarray(data['1_10000__map_mean']))
+
+
+def workload_name(args):
+    return ('configs[1]: batch of {} synthetic {}x{} luma images per GPU, fixed-delta Kodak EAE (6 GDN/IGDN, '
+            'random-init weights seed 0), bin width 1.0, shipped table 1_10000/binary_probabilities_1, '
+            'map_mean 1_10000').format(args.batch, args.height, args.width)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle / reference on the host cores
+
+def _cpu_code_one(job):
+    from oracle import coder
+    (planar, table, which) = job
+    (err, out, bits) = coder.compress_maps_planar(planar, table, which=which)
+    assert err == 0 and numpy.array_equal(out, planar)
+    return int(bits.sum())
+
+
+def cpu_pipeline(images, weights, table, map_mean, cores, pool, which):
+    """CPU restatement of one batch: encoder -> centre/quantize -> coder (encode + decode per map, as the
+    reference's compress_lossless does) -> decoder -> cast. Returns (seconds, bits, reconstruction)."""
+    import torch
+    from oracle import glue, transforms
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    rec = numpy.zeros(images.shape, dtype=numpy.uint8)
+    bits = 0
+    mean = map_mean.reshape((1, 1, 1, -1))
+    for i0 in range(0, images.shape[0], 4):          # reconstructing_eae_kodak.py:624 batch_size = 4
+        x = images[i0:i0 + 4, :, :, None].astype(numpy.float32)
+        y = transforms.encoder(x, weights, False)
+        cq = glue.quantize_per_map(y - mean, numpy.ones(128, dtype=numpy.float32))
+        idx = glue.cast_float_to_int16(cq)
+        planar = [numpy.ascontiguousarray(idx[j].reshape(-1, 128).T) for j in range(idx.shape[0])]
+        bits += sum(pool.map(_cpu_code_one, [(p, table, which) for p in planar]))
+        rec[i0:i0 + 4] = glue.cast_bt601(transforms.decoder(cq + mean, weights, False))[..., 0]
+    return (time.perf_counter() - t0, bits, rec)
+
+
+def run_cpu_arm(args, steps, warmup):
+    from autoencoder_based_image_compression_b200 import synthetic
+    from autoencoder_based_image_compression_b200 import weights as wts
+    from oracle import coder
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or max(4, min(cores, 16))
+    which = 'ref' if coder.has_ref() else 'port'
+    coder.build()
+    (table, map_mean) = load_tables()
+    weights = wts.random_init(0, False)
+    images = synthetic.synthetic_luma(numpy.random.default_rng(1), sample, args.height, args.width)
+    with multiprocessing.get_context('fork').Pool(cores) as pool:
+        for _ in range(warmup):
+            cpu_pipeline(images[:4], weights, table, map_mean, cores, pool, which)
+        seconds = 0.
+        for _ in range(steps):
+            seconds += cpu_pipeline(images, weights, table, map_mean, cores, pool, which)[0]
+    value = sample*steps/seconds
+    return {'value': value, 'unit': 'images/s', 'cores': cores,
+            'kind': 'port',
+            'sample': ('{} images of {}x{} per step x {} steps; transforms = torch-CPU fp32 restatement of the TF '
+                       'graph (TensorFlow unavailable offline), coder = {} (encode + in-call decode), one image per '
+                       'worker process').format(sample, args.height, args.width, steps,
+                                                "reference C++ from oracle/_ref" if which == 'ref' else 'C port'),
+            'ms_per_image': 1e3*seconds/(sample*steps)}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        self.gpu_index = gpu_index
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
+                                          '-i', str(gpu_index), '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        clocks = []
+        reasons = set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(',')]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        clocks.append(float(parts[1]))
+                        out['sm_max_mhz'] = float(parts[2])
+                    except ValueError:
+                        continue
+                    for (name, val) in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                           parts[5:9]):
+                        if val.lower().startswith('active'):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if clocks:
+            # under load = the upper half of the samples (the sampler also sees idle gaps)
+            clocks.sort()
+            out['sm_mhz'] = float(numpy.median(clocks[len(clocks)//2:]))
+            out['samples'] = len(clocks)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+
+def run_gpu_arm(args):
+    from autoencoder_based_image_compression_b200 import _native
+    from autoencoder_based_image_compression_b200 import codec as native_codec
+    from autoencoder_based_image_compression_b200 import parallel, synthetic
+    from autoencoder_based_image_compression_b200 import weights as wts
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    lib = _native.lib()
+    _native.require_gpu()
+    torch = None
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _native.check(lib.eae_set_device(local_rank))
+
+    (n, h, w) = (args.batch, args.height, args.width)
+    (table, map_mean) = load_tables()
+    weights = wts.random_init(0, False)
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), table, map_mean)
+    native_params = params.native()
+    codec = native_codec.Codec(weights, False, device=local_rank, math=args.math)
+
+    # Inputs rotate over enough distinct batches to exceed the L2 (each step also streams ~0.7 GB of
+    # fp32 activations through HBM), so no step finds its input cached from the previous one.
+    batch_bytes = n*h*w
+    rotate = max(2, -(-(L2_BYTES + batch_bytes)//batch_bytes))
+    rng = numpy.random.default_rng(1000 + rank)
+    host_images = _native.pinned_empty((rotate, n, h, w), numpy.uint8)
+    base = synthetic.synthetic_luma(rng, n, h, w)
+    for r in range(rotate):
+        host_images[r] = numpy.roll(base, shift=(r, 7*r, 13*r), axis=(0, 1, 2))
+    bound = int(lib.eae_container_bound(n, h, w, params.truncated_unary_length))
+    d_images = lib.eae_device_alloc(rotate*batch_bytes)
+    d_container = lib.eae_device_alloc(bound)
+    d_recon = lib.eae_device_alloc(batch_bytes)
+    d_total = lib.eae_device_alloc(8)
+    if world > 1:
+        stats_t = torch.zeros(130, dtype=torch.int64, device='cuda')
+        d_stats = stats_t.data_ptr()
+    else:
+        d_stats = lib.eae_device_alloc(ctypes.sizeof(_native.BatchStats))
+    _native.check(lib.eae_memcpy_h2d(d_images, _native.ptr(host_images), rotate*batch_bytes, None))
+    _native.check(lib.eae_stream_synchronize(None))
+
+    def step_dev(i):
+        img = d_images + (i % rotate)*batch_bytes
+        _native.check(lib.eae_compress_dev(codec.handle, ctypes.byref(native_params), img, n, h, w, d_container, bound,
+                                           d_total, d_stats, None))
+        if world > 1:
+            dist.all_reduce(stats_t)     # per-map bit totals over all ranks (NCCL over NVLink)
+        _native.check(lib.eae_decompress_dev(codec.handle, ctypes.byref(native_params), d_container, n, h, w, d_recon,
+                                             None))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        _native.check(lib.eae_stream_synchronize(None))
+
+    ev0 = ctypes.c_void_p()
+    ev1 = ctypes.c_void_p()
+    _native.check(lib.eae_event_create(ctypes.byref(ev0)))
+    _native.check(lib.eae_event_create(ctypes.byref(ev1)))
+
+    # ---- device-resident timing ----
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.eae_profile_reset()
+    lib.eae_profile_enable(1)
+    launches0 = lib.eae_launch_count()
+    _native.check(lib.eae_event_record(ev0, None))
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    _native.check(lib.eae_event_record(ev1, None))
+    barrier()
+    ms = ctypes.c_float(0.)
+    _native.check(lib.eae_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    launches = lib.eae_launch_count() - launches0
+    lib.eae_profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+    profile = {}
+    for cls in range(11):
+        cnt = ctypes.c_uint64(0)
+        tot = ctypes.c_double(0.)
+        lib.eae_profile_read(cls, ctypes.byref(cnt), ctypes.byref(tot))
+        profile[lib.eae_profile_name(cls).decode()] = (int(cnt.value), float(tot.value))
+    dev_ms = parallel.max_over_ranks(ms.value)
+
+    # sanity of the timed work: the last step's container size, statistics and reconstruction
+    total = numpy.zeros(1, dtype=numpy.uint64)
+    _native.check(lib.eae_memcpy_d2h(_native.ptr(total), d_total, 8, None))
+    recon = numpy.empty((n, h, w), dtype=numpy.uint8)
+    _native.check(lib.eae_memcpy_d2h(_native.ptr(recon), d_recon, batch_bytes, None))
+    _native.check(lib.eae_stream_synchronize(None))
+    last = host_images[(args.warmup + args.steps - 1) % rotate]
+    sse = float(((recon.astype(numpy.int64) - last.astype(numpy.int64))**2).sum())
+    if total[0] <= 32 + 8*128*n or recon.min() < 16 or recon.max() > 235:
+        raise RuntimeError('bench: the timed pipeline produced an implausible result')
+
+    # ---- end-to-end timing through the public host API (pinned host buffers) ----
+    host_container = _native.pinned_empty((bound,), numpy.uint8)
+    host_recon = _native.pinned_empty((n, h, w), numpy.uint8)
+    h2d = 0
+    d2h = 0
+
+    def step_e2e(i):
+        blob = codec.compress(host_images[i % rotate], params, container=host_container)
+        codec.decompress(blob, params, out=host_recon)
+        return blob.size
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    _native.check(lib.eae_event_record(ev0, None))
+    blob_bytes = 0
+    for i in range(args.steps):
+        blob_bytes += step_e2e(args.warmup + i)
+    _native.check(lib.eae_event_record(ev1, None))
+    barrier()
+    e2e_wall_ms = 1e3*(time.perf_counter() - t0)
+    _native.check(lib.eae_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+    e2e_ms = parallel.max_over_ranks(max(ms.value, 0.))
+    e2e_wall_ms = parallel.max_over_ranks(e2e_wall_ms)
+    h2d = batch_bytes + blob_bytes//args.steps
+    d2h = blob_bytes//args.steps + batch_bytes + 8 + 8 + ctypes.sizeof(_native.BatchStats)
+
+    images_total = n*world*args.steps
+    line = {
+        'metric': METRIC,
+        'value': images_total/(dev_ms/1e3),
+        'unit': 'images/s',
+        'n_gpus': world,
+        'steps': args.steps,
+        'warmup': args.warmup,
+        'ms_per_step': dev_ms/args.steps,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f32' if args.math == 'fp32' else args.math,
+        'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'batch_per_gpu': n, 'math': args.math,
+                   'l2': 'inputs rotate over {} distinct batches ({} MB > 126 MB L2); every step also streams about '
+                         '{} MB of fp32 activations'.format(rotate, rotate*batch_bytes >> 20, 29*n),
+                   'parallelism': 'images sharded over {} GPU(s), no data-path collective, one NCCL all-reduce of '
+                                  'int64[130] rate statistics per step'.format(world)},
+        'mpixel_per_s': images_total*h*w/1e6/(dev_ms/1e3),
+        'gpu_launches': int(launches),
+        'e2e': {'value': images_total/(max(e2e_ms, e2e_wall_ms)/1e3), 'unit': 'images/s',
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step_events': e2e_ms/args.steps, 'ms_per_step_wall': e2e_wall_ms/args.steps},
+        'rate_bpp': float(total[0] - 32 - 8*128*n)*8./(n*h*w),
+        'psnr_db_random_weights': float(10.*numpy.log10(255.**2/(sse/(n*h*w)))) if sse > 0 else None,
+        'stage_ms_per_step': {k: v[1]/args.steps for (k, v) in profile.items()},
+    }
+    if clocks is not None:
+        line['clocks'] = {'sm_mhz': clocks['sm_mhz'], 'sm_max_mhz': clocks['sm_max_mhz'], 'reasons': clocks['reasons']}
+
+    # ---- roofline of the dominant kernel: the tap-list GEMM (all four gemm_* classes are one kernel) ----
+    scale = (h*w)/(512.*768.)
+    gemm_ms = sum(profile[k][1] for k in GFLOP_PER_IMAGE)
+    gemm_launches = sum(profile[k][0] for k in GFLOP_PER_IMAGE)
+    gflop = sum(GFLOP_PER_IMAGE.values())*scale*n*args.steps
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    (bf16_peak, peak_src) = (1590., 'fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)')
+    if os.path.isfile(peaks_path):
+        with open(peaks_path) as f:
+            bf16_peak = float(json.load(f)['bf16_tflops'])
+        peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)'
+    achieved = gflop/gemm_ms if gemm_ms > 0 else 0.     # GFLOP / ms = TFLOP/s
+    line['roofline'] = {
+        'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
+        'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',
+        'frac': achieved/(bf16_peak/2.) if bf16_peak else None, 'traffic': None,
+        'peak_source': peak_src + ' / 2: tcgen05 kind::tf32 runs at half the bf16 rate; fp32 data, so the TF32 '
+                                  'tensor peak is the bound the north star names',
+        'algorithmic_gflop_per_step': gflop/args.steps, 'launches_per_step': gemm_launches/args.steps,
+        'avg_launch_ms': gemm_ms/gemm_launches if gemm_launches else None,
+        'share_of_step': gemm_ms/dev_ms if dev_ms else None,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = run_cpu_arm(args, steps=1, warmup=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        base = run_cpu_arm(args, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'images/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': base['ms_per_image'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(args), 'batch_per_gpu': args.batch},
+                'cpu_baseline': base, 'gpu_launches': 0,
+                'e2e': {'value': base['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+    run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

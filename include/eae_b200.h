@@ -15,7 +15,7 @@
  * There is NO CPU fallback anywhere behind this ABI: without a CUDA device every compute entry
  * point returns -10.
  *
- * "Reference" citations are relative to /root/reference/kodak_tensorflow/.
+ * "Reference" citations are relative to the kodak_tensorflow/ directory of the reference repository.
  *
  * Memory spaces: functions suffixed _host take host pointers and perform the H2D / D2H copies
  * themselves on the given stream and synchronise it before returning. Functions suffixed _dev take
@@ -60,6 +60,19 @@ int eae_device_count(void);
 int eae_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 /* Cumulative number of kernels this library has launched in this process (bench: gpu_launches). */
 uint64_t eae_launch_count(void);
+
+/* Selects the device used by the entry points that take no codec (coder / glue); codecs carry their own. */
+int eae_set_device(int device);
+
+/* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of
+ * a class). Classes: 0 gemm_conv (k5 s2 convolutions), 1 gemm_tconv (k5 s2 transposed convolutions),
+ * 2 gemm_gdn, 3 gemm_thin (first / last layer contractions), 4 im2col, 5 col2im, 6 quantize,
+ * 7 dequantize, 8 coder_encode, 9 coder_decode, 10 pack. eae_profile_read synchronises the device. */
+#define EAE_PROFILE_CLASSES 11
+int eae_profile_enable(int on);
+int eae_profile_reset(void);
+int eae_profile_read(int kernel_class, uint64_t* launches, double* total_ms);
+const char* eae_profile_name(int kernel_class);
 
 /* Pinned host memory and device memory helpers for callers without a CUDA binding. */
 void* eae_host_alloc(size_t bytes);

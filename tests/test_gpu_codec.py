@@ -1,0 +1,120 @@
+"""The fused pipeline (encode -> quantize -> lossless code -> container -> decode) against the oracle:
+bitstreams byte-identical given identical indices, indices >= 99.99 % identical, PSNR within 0.01 dB,
+rate within 0.1 % (BASELINE.json north_star; configs 1-3 at test scale)."""
+import numpy
+import pytest
+import torch
+
+from autoencoder_based_image_compression_b200 import codec as native_codec
+from autoencoder_based_image_compression_b200 import weights as wts
+from oracle import coder as oracle_coder
+from oracle import glue as oracle_glue
+from oracle import transforms as T
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_pipeline(lum, w, learned, params):
+    """CPU restatement of reconstructing_eae_kodak.py:144-224 for one batch."""
+    y = T.encoder(lum[..., None].astype(numpy.float32), w, learned)
+    mean = params.map_mean if params.map_mean is not None else numpy.zeros(128, dtype=numpy.float32)
+    centered = y - mean.reshape((1, 1, 1, -1))
+    cq = oracle_glue.quantize_per_map(centered, params.bin_widths)
+    idx = oracle_glue.cast_float_to_int16(cq/params.bin_widths.reshape((1, 1, 1, -1)))
+    rec = oracle_glue.cast_bt601(T.decoder(cq + mean.reshape((1, 1, 1, -1)), w, learned))[..., 0]
+    return (y, idx, rec)
+
+
+@pytest.mark.parametrize('learned', [False, True])
+def test_round_trip_and_byte_identity(native, golden, learned):
+    rng = numpy.random.default_rng(3)
+    w = wts.random_init(0, learned)
+    (n, h, wd) = (3, 128, 192)
+    lum = util.synthetic_luma(rng, n, h, wd)
+    model = 'learning_bw_0dot5_10000' if learned else '1_10000'
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table(model, '1'),
+                                       0.05*golden.map_mean(model))
+    codec = native_codec.Codec(w, learned)
+    (blob, stats) = codec.compress(lum, params, return_stats=True)
+    idx_gpu = codec.last_indices(n, h, wd)                       # [n, 128, hw]
+    (info, streams) = native_codec.parse_container(blob)
+    assert info['n'] == n and info['h'] == h and info['w'] == wd and info['L'] == 10 and info['bytes'] == blob.size
+    # (1) bitstreams byte-identical to the CPU coder on the same indices, every stream
+    total = 0
+    for s in range(n*128):
+        want = oracle_coder.encode_map(idx_gpu.reshape(n*128, -1)[s], params.table[s % 128], 'port')
+        assert want[0] == 0
+        (bb, rb, bac, byp) = streams[s]
+        assert (bb, rb) == (want[2], want[4])
+        assert numpy.array_equal(bac, want[1]) and numpy.array_equal(byp, want[3])
+        total += bb + rb
+    assert stats['total_bits'] == total
+    assert numpy.array_equal(stats['bits_per_map'],
+                             numpy.array([sum(streams[i*128 + m][0] + streams[i*128 + m][1] for i in range(n))
+                                          for m in range(128)], dtype=numpy.uint64))
+    # (2) indices vs the oracle's
+    (y_ref, idx_ref, rec_ref) = oracle_pipeline(lum, w, learned, params)
+    idx_ref_planar = idx_ref.reshape(n, -1, 128).transpose(0, 2, 1)
+    agree = (idx_gpu == idx_ref_planar).mean()
+    assert agree >= 0.9999, agree
+    assert numpy.abs(idx_gpu.astype(numpy.int32) - idx_ref_planar).max() <= 1
+    dead_ref = int(oracle_glue.count_nb_deads(idx_ref.astype(numpy.float32)).sum())
+    assert abs(stats['nb_dead_maps'] - dead_ref) <= 1
+    # (3) decompress: exact inverse of the coder, reconstruction close to the oracle's
+    rec = codec.decompress(blob, params)
+    assert rec.shape == (n, h, wd) and rec.dtype == numpy.uint8
+    assert numpy.array_equal(codec.last_indices(n, h, wd), idx_gpu)
+    for i in range(n):
+        assert abs(oracle_glue.psnr_2d(lum[i], rec[i]) - oracle_glue.psnr_2d(lum[i], rec_ref[i])) < 0.01
+    # rate within 0.1 % of the oracle's coder on the oracle's indices
+    bits_ref = 0
+    for i in range(n):
+        for m in range(128):
+            bits_ref += oracle_coder.compress_lossless(idx_ref[i, :, :, m].flatten(), params.table[m], 'port')[2]
+    assert abs(total - bits_ref) <= 1e-3*bits_ref
+
+
+def test_quantization_sweep(native, golden):
+    """BASELINE config 3 at test scale: one EAE, bin widths delta x {1, 2, 4, 8}."""
+    rng = numpy.random.default_rng(4)
+    w = wts.random_init(0, False)
+    lum = util.synthetic_luma(rng, 2, 128, 128)
+    codec = native_codec.Codec(w, False)
+    rates = []
+    psnrs = []
+    for mult in (1, 2, 4, 8):
+        params = native_codec.CodingParams(mult*numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', str(mult)))
+        (blob, stats) = codec.compress(lum, params, return_stats=True)
+        rec = codec.decompress(blob, params)
+        (_, idx_ref, rec_ref) = oracle_pipeline(lum, w, False, params)
+        bits_ref = sum(oracle_coder.compress_lossless(idx_ref[i, :, :, m].flatten(), params.table[m], 'port')[2]
+                       for i in range(2) for m in range(128))
+        assert abs(stats['total_bits'] - bits_ref) <= 1e-3*bits_ref
+        for i in range(2):
+            assert abs(oracle_glue.psnr_2d(lum[i], rec[i]) - oracle_glue.psnr_2d(lum[i], rec_ref[i])) < 0.01
+        rates.append(stats['total_bits'])
+        psnrs.append(oracle_glue.psnr_2d(lum[0], rec[0]))
+    assert rates == sorted(rates, reverse=True)       # coarser bins never cost more bits
+
+
+def test_container_errors(native, golden):
+    w = wts.random_init(0, True)
+    codec = native_codec.Codec(w, True)
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'))
+    lum = util.synthetic_luma(numpy.random.default_rng(5), 1, 64, 64)
+    blob = codec.compress(lum, params).copy()
+    with pytest.raises(RuntimeError):       # truncated payload -> resource error (code 2)
+        codec.decompress(blob[:-40], params)
+    bad = blob.copy()
+    bad[0] ^= 0xFF
+    with pytest.raises(ValueError):
+        codec.decompress(bad, params)
+    with pytest.raises(ValueError):         # bin width <= 0 (tools.py:924-925)
+        codec.compress(lum, native_codec.CodingParams(numpy.zeros(128, dtype=numpy.float32), golden.table('1_10000', '1')))
+    nan_table = golden.table('1_10000', '1').copy()
+    nan_table[:, 0] = numpy.nan
+    with pytest.raises(RuntimeError, match='Error of type 4'):
+        codec.compress(lum, native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), nan_table))
+    with pytest.raises(ValueError):         # EntropyAutoencoder.py:77-80
+        codec.compress(numpy.zeros((1, 40, 64), dtype=numpy.uint8), params)

@@ -1,0 +1,158 @@
+"""Host-side logic of the Python mirror of the reference interface: argument validation raises the
+reference's exceptions before anything reaches the GPU; sharding helpers; container parsing."""
+import numpy
+import pytest
+
+from autoencoder_based_image_compression_b200 import codec as native_codec
+from autoencoder_based_image_compression_b200 import parallel
+from autoencoder_based_image_compression_b200 import weights as wts
+from autoencoder_based_image_compression_b200.kodak_tensorflow.eae import batching
+from autoencoder_based_image_compression_b200.kodak_tensorflow.eae.graph import constants as csts
+from autoencoder_based_image_compression_b200.kodak_tensorflow.eae.graph.EntropyAutoencoder import EntropyAutoencoder
+from autoencoder_based_image_compression_b200.kodak_tensorflow.eae.graph.IsolatedDecoder import IsolatedDecoder
+from autoencoder_based_image_compression_b200.kodak_tensorflow.lossless import compression, interface_cython
+from autoencoder_based_image_compression_b200.kodak_tensorflow.tools import tools as tls
+
+
+def test_constants():
+    assert (csts.NB_MAPS_1, csts.NB_MAPS_2, csts.NB_MAPS_3) == (128, 128, 128)
+    assert (csts.WIDTH_KERNEL_1, csts.WIDTH_KERNEL_2, csts.WIDTH_KERNEL_3) == (9, 5, 5)
+    assert csts.STRIDE_PROD == 16
+
+
+def test_weights_random_init_and_npz(tmp_path):
+    for learned in (False, True):
+        w = wts.random_init(0, learned, bin_width_init=0.5)
+        wts.validate(w, learned)
+        assert w['encoder/weights_1'].shape == (9, 9, 1, 128) and w['decoder/weights_6'].shape == (9, 9, 1, 128)
+        assert numpy.allclose(w['encoder/gamma_1'], w['encoder/gamma_1'].T) and w['encoder/gamma_1'].min() >= 2e-5
+        assert numpy.all(w[wts.BIN_WIDTHS_KEY] == numpy.float32(0.5))
+        assert ('decoder/gamma_4' in w) == (not learned)
+    path = str(tmp_path/'model.npz')
+    wts.save(path, w)
+    back = wts.load(path)
+    assert sorted(back) == sorted(w) and all(numpy.array_equal(back[k], w[k]) for k in w)
+    del w['decoder/weights_6']
+    with pytest.raises(KeyError):
+        wts.validate(w, True)
+
+
+def test_model_classes_validate_like_the_reference():
+    with pytest.raises(ValueError):     # EntropyAutoencoder.py:77-80
+        EntropyAutoencoder(4, 500, 768, 1., 10000., '', False)
+    with pytest.raises(ValueError):     # IsolatedDecoder.py:50-53
+        IsolatedDecoder(4, 512, 770, False)
+    ae = EntropyAutoencoder(4, 512, 768, 1., 10000., '', True)
+    with pytest.raises(RuntimeError):
+        ae.get_bin_widths()
+    ae.initialization(None, '')
+    assert ae.get_bin_widths().dtype == numpy.float32 and ae.get_bin_widths().shape == (128,)
+
+
+def test_batching_argument_checks():
+    ae = EntropyAutoencoder(4, 32, 48, 1., 10000., '', False)
+    ae.initialization(None, '')
+    with pytest.raises(TypeError):      # batching.py:86-87
+        batching.encode_mini_batches(numpy.zeros((4, 32, 48, 1), dtype=numpy.float32), None, ae, 4)
+    with pytest.raises(ValueError):     # tools.py:1130-1131
+        batching.encode_mini_batches(numpy.zeros((6, 32, 48, 1), dtype=numpy.uint8), None, ae, 4)
+    with pytest.raises(ValueError):     # unpacking of a 3D array (batching.py:91)
+        batching.encode_mini_batches(numpy.zeros((4, 32, 48), dtype=numpy.uint8), None, ae, 4)
+    dec = IsolatedDecoder(4, 32, 48, False)
+    dec.initialization(None, '')
+    with pytest.raises(ValueError):
+        batching.decode_mini_batches(numpy.zeros((3, 2, 3, 128), dtype=numpy.float32), None, dec, 2)
+
+
+def test_tools_argument_checks():
+    with pytest.raises(ValueError):     # tools.py:917-918
+        tls.quantize_per_map(numpy.zeros((1, 2, 2, 4), dtype=numpy.float32), numpy.ones((4, 1), dtype=numpy.float32))
+    with pytest.raises(ValueError):     # :922-923
+        tls.quantize_per_map(numpy.zeros((1, 2, 2, 4), dtype=numpy.float32), numpy.ones(3, dtype=numpy.float32))
+    with pytest.raises(ValueError):     # :924-925
+        tls.quantize_per_map(numpy.zeros((1, 2, 2, 4), dtype=numpy.float32), numpy.array([1, 1, 0, 1], dtype=numpy.float32))
+    with pytest.raises(TypeError):      # :91-92
+        tls.cast_bt601(numpy.zeros(4, dtype=numpy.int32))
+    with pytest.raises(TypeError):      # :124-125
+        tls.cast_float_to_int16(numpy.zeros(4, dtype=numpy.uint8))
+    with pytest.raises(TypeError):      # :866-867
+        tls.psnr_2d(numpy.zeros((2, 2), dtype=numpy.float32), numpy.zeros((2, 2), dtype=numpy.uint8))
+    with pytest.raises(ValueError):     # :870-873
+        tls.psnr_2d(numpy.zeros((2, 2, 1), dtype=numpy.uint8), numpy.zeros((2, 2, 1), dtype=numpy.uint8))
+    with pytest.raises(ValueError):     # :313-314
+        tls.count_nb_deads(numpy.zeros((2, 2, 2), dtype=numpy.float32))
+    with pytest.raises(ValueError):
+        tls.subdivide_set(10, 4)
+    assert tls.subdivide_set(24, 4) == 6
+
+
+def test_lossless_argument_checks(tmp_path):
+    with pytest.raises(TypeError):      # compression.py:52-53
+        compression.compress_lossless_maps(numpy.zeros((2, 2, 3), dtype=numpy.int32), 'unused.npy')
+    path = str(tmp_path/'table.npy')
+    numpy.save(path, numpy.full((4, 10), 0.5))
+    with pytest.raises(ValueError):     # :63-64
+        compression.compress_lossless_maps(numpy.zeros((2, 2, 3), dtype=numpy.int16), path)
+    numpy.save(path, numpy.full(10, 0.5))
+    compression._TABLE_CACHE.clear()
+    with pytest.raises(ValueError):     # :61-62
+        compression.compress_lossless_maps(numpy.zeros((2, 2, 3), dtype=numpy.int16), path)
+    with pytest.raises(ValueError):     # :129-130
+        compression.rescale_compress_lossless_maps(numpy.zeros((2, 2, 3), dtype=numpy.float32),
+                                                   numpy.ones((3, 1), dtype=numpy.float32), path)
+    with pytest.raises(ValueError):     # :135-136
+        compression.rescale_compress_lossless_maps(numpy.zeros((2, 2, 3), dtype=numpy.float32),
+                                                   numpy.ones(4, dtype=numpy.float32), path)
+    with pytest.raises(ValueError):     # Cython buffer dtype mismatch
+        interface_cython.compress_lossless_flattened_map(numpy.zeros(4, dtype=numpy.int32), numpy.full(3, 0.5))
+    with pytest.raises(ValueError):
+        interface_cython.compress_lossless_flattened_map(numpy.zeros((2, 2), dtype=numpy.int16), numpy.full(3, 0.5))
+    with pytest.raises(OverflowError):  # interface_cython.pyx:50-52
+        interface_cython.compress_lossless_flattened_map(numpy.zeros(4, dtype=numpy.int16), numpy.full(256, 0.5))
+
+
+def test_coding_params_checks():
+    with pytest.raises(ValueError):
+        native_codec.CodingParams(numpy.ones(128), numpy.full(10, 0.5))
+    with pytest.raises(ValueError):
+        native_codec.CodingParams(numpy.ones(128), numpy.full((3, 10), 0.5))
+    p = native_codec.CodingParams(numpy.ones(128), numpy.full((128, 10), 0.5), numpy.zeros(128))
+    assert p.truncated_unary_length == 10 and p.native().truncated_unary_length == 10
+
+
+def test_container_parser():
+    n_streams = 128
+    table = numpy.zeros((n_streams, 2), dtype=numpy.uint32)
+    table[:, 0] = 9
+    table[:, 1] = numpy.arange(n_streams) % 17
+    payload = bytearray()
+    for s in range(n_streams):
+        payload += bytes([s % 251])*2 + bytes([7])*((int(table[s, 1]) + 7)//8)
+    hdr = numpy.array([0x42454145, 1, 1, 16, 16, 128, 10, 0], dtype=numpy.uint32)
+    blob = numpy.frombuffer(hdr.tobytes() + table.tobytes() + bytes(payload), dtype=numpy.uint8)
+    (info, streams) = native_codec.parse_container(blob)
+    assert info == {'n': 1, 'h': 16, 'w': 16, 'nb_maps': 128, 'L': 10, 'bytes': blob.size}
+    assert streams[5][0] == 9 and streams[5][2].tolist() == [5, 5] and len(streams[5][3]) == 1
+    with pytest.raises(ValueError):
+        native_codec.parse_container(numpy.zeros(64, dtype=numpy.uint8))
+
+
+def test_shard_range_covers_everything_once():
+    for (n, world) in ((4096, 8), (24, 8), (5, 8), (256, 3), (0, 2)):
+        seen = []
+        for r in range(world):
+            (a, b) = parallel.shard_range(n, r, world)
+            seen += list(range(a, b))
+        assert seen == list(range(n))
+    sizes = [parallel.shard_range(24, r, 5)[1] - parallel.shard_range(24, r, 5)[0] for r in range(5)]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def test_stats_pack_and_summary():
+    vec = parallel.pack_stats(numpy.arange(128), 8128, 3, 1000., 512*768*2, 2)
+    s = parallel.summarize(parallel.unpack_stats(vec))
+    assert s['total_bits'] == 8128 and s['nb_dead_maps'] == 3 and s['nb_images'] == 2
+    assert abs(s['rate_bpp'] - 8128/(512*768*2)) < 1e-15
+    assert abs(s['psnr_db'] - 10*numpy.log10(255**2/(1000./(512*768*2)))) < 1e-12
