@@ -9,6 +9,7 @@
 // fused) followed by floor (BinaryArithmeticCoder.cpp:154).
 #include <memory>
 
+#include "coder_core.cuh"
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -16,188 +17,31 @@ namespace eae {
 
 namespace {
 
-constexpr uint32_t kRangeMax = 0xFFFFu;       // BinaryArithmeticCoder.cpp:14
-constexpr uint32_t kHalf = 0x7FFFu;           // :20
-constexpr uint32_t kQuarter = 0x3FFFu;        // :26
-constexpr uint32_t kThreeQuarters = 0xBFFDu;  // :27  (3 * 0x3FFF, not 0xBFFF)
-constexpr uint32_t kMsb = 0x8000u;            // :33
-
-// LSB-first bit writer: bit i of the stream is bit (i & 7) of byte (i >> 3) (Bitstream.cpp:36-58),
-// i.e. bit (i & 31) of little-endian 32-bit word (i >> 5). The slot is 16-byte aligned.
-struct BitSink {
-    uint32_t* words;
-    uint32_t cap_bits;
-    uint32_t nbits;
-    uint32_t widx;
-    uint32_t fill;
-    uint64_t acc;
-
-    __device__ __forceinline__ void init(uint8_t* slot, uint32_t cap)
-    {
-        words = reinterpret_cast<uint32_t*>(slot);
-        cap_bits = cap; nbits = 0; widx = 0; fill = 0; acc = 0;
-    }
-    // Appends the `count` (1..32) low bits of `value`, first bit = bit 0. False on overflow
-    // (Bitstream.cpp:38-41: capacity_error as soon as one bit does not fit).
-    __device__ __forceinline__ bool put(uint32_t value, uint32_t count)
-    {
-        if (nbits + count > cap_bits) return false;
-        acc |= (uint64_t)value << fill;
-        fill += count;
-        nbits += count;
-        if (fill >= 32) {
-            words[widx++] = (uint32_t)acc;
-            acc >>= 32;
-            fill -= 32;
-        }
-        return true;
-    }
-    // `first` followed by `repeat` copies of !first (E3 follow bits, BinaryArithmeticCoder.cpp:317-337).
-    __device__ __forceinline__ bool put_with_follow(uint32_t first, uint32_t repeat)
-    {
-        uint32_t c = repeat < 31u ? repeat : 31u;
-        uint32_t inv = first ? 0u : ((1u << c) - 1u);
-        if (!put(first | (inv << 1), c + 1)) return false;
-        repeat -= c;
-        while (repeat) {
-            c = repeat < 32u ? repeat : 32u;
-            uint32_t ones = c == 32u ? 0xFFFFFFFFu : ((1u << c) - 1u);
-            if (!put(first ? 0u : ones, c)) return false;
-            repeat -= c;
-        }
-        return true;
-    }
-    __device__ __forceinline__ void flush()
-    {
-        if (fill) words[widx] = (uint32_t)acc;
-    }
-};
-
-// LSB-first bit reader over an arbitrarily aligned byte range.
-struct BitSource {
-    const uint8_t* bytes;
-    uint32_t nbits;   // bits written by the encoder
-    uint32_t rd;      // bits consumed
-    uint32_t nbytes;
-    uint32_t bpos;    // next byte to load
-    uint32_t fill;
-    uint64_t acc;
-
-    __device__ __forceinline__ void init(const uint8_t* p, uint32_t bits)
-    {
-        bytes = p; nbits = bits; rd = 0; nbytes = (bits + 7) >> 3; bpos = 0; fill = 0; acc = 0;
-    }
-    __device__ __forceinline__ bool exhausted() const { return rd >= nbits; }
-    // Caller guarantees !exhausted().
-    __device__ __forceinline__ uint32_t get()
-    {
-        if (fill == 0) {
-            #pragma unroll 1
-            while (fill <= 56 && bpos < nbytes) {
-                acc |= (uint64_t)__ldg(bytes + bpos) << fill;
-                bpos++;
-                fill += 8;
-            }
-        }
-        uint32_t bit = (uint32_t)acc & 1u;
-        acc >>= 1;
-        fill--;
-        rd++;
-        return bit;
-    }
-};
-
-// middle = low + (uint32_t)floor(p * (high - low))   (BinaryArithmeticCoder.cpp:144-156)
-__device__ __forceinline__ uint32_t split_point(uint32_t low, uint32_t high, double p)
-{
-    return low + __double2uint_rd(__dmul_rn(p, (double)(high - low)));
-}
-
-// ------------------------------------------------------------------------------------------------
-// Encoder: LosslessCoder::write_signed_ueg0 per symbol (LosslessCoder.cpp:232-252), then
-// BinaryArithmeticCoder::stop_encoding (BinaryArithmeticCoder.cpp:61-102).
-__global__ void __launch_bounds__(64)
+// One stream per `lanes` consecutive threads (only the first of them works). lanes = 32 gives every
+// stream its own warp: no divergence and the most warps in flight, which is what a small batch needs
+// because the coder is latency-bound; lanes = 1 packs 32 streams per warp for the best issue efficiency
+// when there are far more streams than warp slots. launch_* pick `lanes` from the stream count.
+__global__ void __launch_bounds__(64, 8)
 encode_streams_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint32_t size,
                       const double* __restrict__ table, uint32_t table_rows, uint32_t L,
                       const uint8_t* __restrict__ skip_mask, uint8_t* __restrict__ bac_slots,
                       uint8_t* __restrict__ byp_slots, uint32_t slot_bytes, uint32_t cap_bits,
                       uint32_t* __restrict__ bac_bits, uint32_t* __restrict__ byp_bits,
-                      uint32_t* __restrict__ err)
+                      uint32_t* __restrict__ err, uint32_t lanes)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t s = t / lanes;
     if (s >= n_streams) return;
     const uint32_t row = s % table_rows;
     if (skip_mask && skip_mask[row]) {
         bac_bits[s] = 0; byp_bits[s] = 0; err[s] = 0;
         return;
     }
-    const int16_t* __restrict__ src = idx + (size_t)s * size;
-    const double* __restrict__ prob = table + (size_t)row * L;
-
-    BitSink bac, byp;
+    core::BitSink bac, byp;
     bac.init(bac_slots + (size_t)s * slot_bytes, cap_bits);
     byp.init(byp_slots + (size_t)s * slot_bytes, cap_bits);
-
-    uint32_t low = 0, high = kRangeMax, pending = 0;
-    uint32_t e = 0;
-    uint32_t i = 0;                   // next symbol
-    uint32_t ones = 0, nb = 0, bin = 0;  // prefix of the current symbol: `ones` 1s then a 0 iff nb > ones
-
-    #pragma unroll 1
-    while (true) {
-        if (bin == nb) {
-            if (i == size) break;
-            const int v = (int)__ldg(src + i);
-            i++;
-            const uint32_t a = (uint32_t)(v < 0 ? -v : v);
-            ones = a < L ? a : L;
-            nb = ones + (a < L ? 1u : 0u);
-            bin = 0;
-            // Bypass bits of this symbol: EG0(a - L) if a >= L (LosslessCoder.cpp:58-111), then the
-            // sign, 0 = negative (LosslessCoder.cpp:22-37). At most 31 + 1 bits.
-            uint32_t code = 0, cnt = 0;
-            if (a >= L) {
-                const uint32_t x1 = a - L + 1u;
-                const uint32_t n = 31u - (uint32_t)__clz((int)x1);
-                code = (1u << n) - 1u;                       // n ones, then a zero at position n
-                if (n) code |= (__brev(x1 - (1u << n)) >> (32u - n)) << (n + 1u);  // suffix MSB first
-                cnt = 2u * n + 1u;
-            }
-            if (v != 0) { code |= (v > 0 ? 1u : 0u) << cnt; cnt++; }
-            if (cnt && !byp.put(code, cnt)) { e = EAE_ERR_CAPACITY; break; }
-        }
-        // One truncated-unary bin through the arithmetic coder (LosslessCoder.cpp:167-191,
-        // BinaryArithmeticCoder.cpp:49-59, 158-252).
-        const double p = __ldg(prob + bin);
-        if (!(p > 0.0 && p < 1.0)) { e = EAE_ERR_PROBABILITY; break; }   // also catches NaN (:146-153)
-        const uint32_t mid = split_point(low, high, p);
-        if (bin < ones) low = mid + 1u; else high = mid;
-        if (high > kRangeMax || low > kRangeMax) { e = EAE_ERR_PRECISION; break; }
-        bool ok = true;
-        #pragma unroll 1
-        while (true) {
-            if (((low ^ high) & kMsb) == 0u) {               // E1 / E2: MSBs agree, emit it
-                const uint32_t top = high >> 15;
-                low = (low & kHalf) << 1;
-                high = ((high & kHalf) << 1) | 1u;
-                ok = bac.put_with_follow(top, pending);
-                pending = 0;
-                if (!ok) break;
-            } else if (low > kQuarter && high <= kThreeQuarters) {   // E3
-                low = (low - (kQuarter + 1u)) << 1;
-                high = ((high - (kQuarter + 1u)) << 1) | 1u;
-                pending++;
-            } else {
-                break;
-            }
-        }
-        if (!ok) { e = EAE_ERR_CAPACITY; break; }
-        bin++;
-    }
-    if (!e) {
-        // stop_encoding: one more pending bit, 0 + ones if low < QUARTER else 1 + zeros.
-        if (!bac.put_with_follow(low < kQuarter ? 0u : 1u, pending + 1u)) e = EAE_ERR_CAPACITY;
-    }
+    const uint32_t e = core::encode_stream(idx + (size_t)s * size, size, table + (size_t)row * L, L, bac, byp);
     bac.flush();
     byp.flush();
     bac_bits[s] = bac.nbits;
@@ -205,93 +49,32 @@ encode_streams_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint3
     err[s] = e;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Decoder: BinaryArithmeticCoder::start_decoding (:104-122) then LosslessCoder::read_signed_ueg0 per
-// symbol (LosslessCoder.cpp:254-276).
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 8)
 decode_streams_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
                       const double* __restrict__ table, uint32_t table_rows, uint32_t L,
                       const uint8_t* __restrict__ skip_mask, const uint8_t* __restrict__ bac_base,
                       const uint64_t* __restrict__ bac_off, const uint32_t* __restrict__ bac_bits,
                       const uint8_t* __restrict__ byp_base, const uint64_t* __restrict__ byp_off,
-                      const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err)
+                      const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err, uint32_t lanes)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t s = t / lanes;
     if (s >= n_streams) return;
     const uint32_t row = s % table_rows;
     if (skip_mask && skip_mask[row]) { err[s] = 0; return; }
-    const double* __restrict__ prob = table + (size_t)row * L;
-    int16_t* __restrict__ dst = out + (size_t)s * size;
-
-    BitSource bac, byp;
+    core::BitSource bac, byp;
     bac.init(bac_base + bac_off[s], bac_bits[s]);
     byp.init(byp_base + byp_off[s], byp_bits[s]);
+    err[s] = core::decode_stream(out + (size_t)s * size, size, table + (size_t)row * L, L, bac, byp);
+}
 
-    uint32_t low = 0, high = kRangeMax, code = 0;
-    {   // 16 bits MSB-first; a short stream is padded with the last bit read (:107-121)
-        uint32_t keep = 0;
-        for (int k = 0; k < 16; k++) {
-            if (!bac.exhausted()) keep = bac.get();
-            code = (code << 1) | keep;
-        }
-    }
-    uint32_t e = 0;
-    #pragma unroll 1
-    for (uint32_t i = 0; i < size && !e; i++) {
-        uint32_t a = 0, bit = 0;
-        #pragma unroll 1
-        for (uint32_t bin = 0;; bin++) {
-            const double p = __ldg(prob + bin);
-            if (!(p > 0.0 && p < 1.0)) { e = EAE_ERR_PROBABILITY; break; }
-            const uint32_t mid = split_point(low, high, p);
-            // decode_bit (:254-273): `bit` keeps its previous value when code is outside [low, high].
-            if (code >= low && code <= mid) { high = mid; bit = 0; }
-            else if (code > mid && code <= high) { low = mid + 1u; bit = 1; }
-            // rescale_decoding (:275-315)
-            uint32_t in = 0;
-            #pragma unroll 1
-            while (true) {
-                if (high <= kHalf) {
-                } else if (low > kHalf) {
-                    high -= kMsb; low -= kMsb; code -= kMsb;
-                } else if (high <= kThreeQuarters && low > kQuarter) {
-                    high -= kQuarter + 1u; low -= kQuarter + 1u; code -= kQuarter + 1u;
-                } else {
-                    break;
-                }
-                if (!bac.exhausted()) in = bac.get();
-                high = ((high << 1) & kRangeMax) | 1u;
-                low = (low << 1) & kRangeMax;
-                code = ((code << 1) & kRangeMax) | in;
-            }
-            if (!bit) break;
-            a++;
-            if (bin == L - 1u) break;
-        }
-        if (e) break;
-        if (a == L) {   // read_eg0 (LosslessCoder.cpp:113-165), uint16_t arithmetic
-            uint32_t n = 0, x = 0;
-            while (true) {
-                if (byp.exhausted()) { e = EAE_ERR_RESOURCE; break; }
-                if (!byp.get()) break;
-                n = (n + 1u) & 0xFFu;
-            }
-            for (uint32_t k = 0; k < n && !e; k++) {
-                if (byp.exhausted()) { e = EAE_ERR_RESOURCE; break; }
-                x = ((x << 1) | byp.get()) & 0xFFFFu;
-            }
-            if (e) break;
-            x = (x + ((1u << (n & 31u)) - 1u)) & 0xFFFFu;
-            a = (a + x) & 0xFFFFu;
-        }
-        int v = (int)(int16_t)(uint16_t)a;
-        if (v != 0) {   // read_sign (LosslessCoder.cpp:39-56)
-            if (byp.exhausted()) { e = EAE_ERR_RESOURCE; break; }
-            if (!byp.get()) v = -v;
-        }
-        dst[i] = (int16_t)v;
-    }
-    err[s] = e;
+// Threads per stream: one warp per stream until that would exceed ~32 warps per SM, then halve.
+inline uint32_t lanes_per_stream(uint32_t n_streams)
+{
+    uint32_t lanes = 32;
+    while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 32ull) lanes >>= 1;
+    return lanes;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,9 +172,10 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
                           cudaStream_t st)
 {
     if (n_streams == 0) return 0;
-    encode_streams_kernel<<<ceil_div_u32(n_streams, 64), 64, 0, st>>>(
+    const uint32_t lanes = lanes_per_stream(n_streams);
+    encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
         idx_planar, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_slots, byp_slots,
-        slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err);
+        slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err, lanes);
     EAE_LAUNCH_OK();
     return 0;
 }
@@ -403,9 +187,10 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
                           const uint32_t* byp_bits, uint32_t* err, cudaStream_t st)
 {
     if (n_streams == 0) return 0;
-    decode_streams_kernel<<<ceil_div_u32(n_streams, 64), 64, 0, st>>>(
+    const uint32_t lanes = lanes_per_stream(n_streams);
+    decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
         idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off,
-        bac_bits, byp_base, byp_off, byp_bits, err);
+        bac_bits, byp_base, byp_off, byp_bits, err, lanes);
     EAE_LAUNCH_OK();
     return 0;
 }

@@ -81,9 +81,11 @@ def _to_indices(quantized_samples, bin_width):
     if bin_width <= 0.:
         raise ValueError('The quantization bin width is not strictly positive.')
     data = numpy.asarray(quantized_samples)
-    scaled = data.astype(numpy.float64)/bin_width
-    idx = cast_float_to_int16(scaled.astype(numpy.float32))
-    numpy.testing.assert_almost_equal(bin_width*idx.astype(numpy.float64), data.astype(numpy.float64), decimal=10,
+    if not _is_float(data.dtype):
+        data = data.astype(numpy.float64)
+    # Same expression and dtype as tools.py:372-375 (float32 data stays float32).
+    idx = cast_float_to_int16(numpy.asarray(data/bin_width, dtype=numpy.float32))
+    numpy.testing.assert_almost_equal(bin_width*idx.astype(data.dtype), data, decimal=10,
                                       err_msg='The quantization was omitted.')
     return idx
 
@@ -160,12 +162,13 @@ def rate_3d(quantized_latent_float32, bin_widths, h_in, w_in):
     if bin_widths.size != nb_maps:
         raise ValueError('`bin_widths.size` is not equal to `quantized_latent_float32.shape[2]`.')
     q = numpy.asarray(quantized_latent_float32)
-    bw = numpy.asarray(bin_widths, dtype=numpy.float64).reshape((1, 1, nb_maps))
+    if not _is_float(q.dtype):
+        q = q.astype(numpy.float64)
+    bw = numpy.asarray(bin_widths).astype(q.dtype).reshape((1, 1, nb_maps))
     if numpy.any(bw <= 0.):
         raise ValueError('The quantization bin width is not strictly positive.')
-    idx = cast_float_to_int16((q.astype(numpy.float64)/bw).astype(numpy.float32))
-    numpy.testing.assert_almost_equal(bw*idx.astype(numpy.float64), q.astype(numpy.float64), decimal=10,
-                                      err_msg='The quantization was omitted.')
+    idx = cast_float_to_int16(numpy.asarray(q/bw, dtype=numpy.float32))
+    numpy.testing.assert_almost_equal(bw*idx.astype(q.dtype), q, decimal=10, err_msg='The quantization was omitted.')
     (mn, mx, hist, _) = _histograms(idx.reshape((1, height_map, width_map, nb_maps)), False)
     cumulated_rate = 0.
     for i in range(nb_maps):
