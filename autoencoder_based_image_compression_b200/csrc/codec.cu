@@ -2,6 +2,7 @@
 // transforms (kodak_tensorflow/eae/graph/components.py:11-142) and the fused
 // encode -> quantize -> lossless code -> container pipeline and its inverse.
 #include <memory>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -16,6 +17,7 @@ struct eae_codec {
     int device = 0;
     int learned = 0;   // are_bin_widths_learned: 4 GDN/IGDN instead of 6
     int math = EAE_MATH_FP32_SIMT;
+    int umma_mask = 0xF;   // which layer kinds run on tensor cores (debug: env EAE_UMMA_LAYERS)
     cudaStream_t own_stream = nullptr;
 
     // ---- weights (device) ----
@@ -147,13 +149,17 @@ int check_dims(uint32_t n, uint32_t h, uint32_t w)
 }
 
 // ---- layer launchers --------------------------------------------------------------------------
-int run_gemm(eae_codec* c, const GemmPlan& plan, int layer_for_umma, cudaStream_t st)
+enum LayerKind : int { kLayerConv = 0, kLayerTconv = 1, kLayerGdn = 2, kLayerThin = 3 };
+
+int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw, cudaStream_t st)
 {
-    ProfScope prof(plan.mode != kEpiBias ? kProfGemmGdn
-                   : (plan.n_taps == 1 ? kProfGemmThin : (plan.out_mul == 2 ? kProfGemmTconv : kProfGemmConv)), st);
-    if (c->math == EAE_MATH_FP32_SIMT || layer_for_umma < 0) return launch_gemm_simt(plan, st);
-    (void)layer_for_umma;
-    return launch_gemm_umma(plan, nullptr, c->math == EAE_MATH_TF32X3, st);
+    static const int prof_of_kind[4] = {kProfGemmConv, kProfGemmTconv, kProfGemmGdn, kProfGemmThin};
+    ProfScope prof(prof_of_kind[kind], st);
+    if (c->math == EAE_MATH_FP32_SIMT || !((c->umma_mask >> kind) & 1)) return launch_gemm_simt(plan, st);
+    // GDN / IGDN always use the split contraction: a single-pass TF32 norm would put a 2^-12 relative
+    // error on every activation, for 4 % of the FLOPs.
+    const bool exact = c->math == EAE_MATH_TF32X3 || kind == kLayerGdn;
+    return launch_gemm_umma(plan, uw, exact, st);
 }
 
 GemmPlan base_plan(const float* in, int Hin, int Win, int Cin, const float* w, const float* bias, float* out,
@@ -171,32 +177,40 @@ GemmPlan base_plan(const float* in, int Hin, int Win, int Cin, const float* w, c
     return p;
 }
 
-// GDN / IGDN as a 1-tap contraction with the squared input (tfutils.py:393-397, 506-509).
-int run_gdn(eae_codec* c, const float* in, float* out, int H, int W, uint32_t n, int which, bool inverse,
-            cudaStream_t st)
+UmmaWeights umma_weights(eae_codec* c, int layer, int n_taps)
 {
-    GemmPlan p = base_plan(in, H, W, 128, c->gamma[which].as<float>(), c->beta[which].as<float>(), out, n);
-    p.mode = inverse ? kEpiIgdn : kEpiGdn;
-    return run_gemm(c, p, -1, st);
+    return UmmaWeights{c->wk_hi[layer].as<float>(), c->wk_lo[layer].as<float>(), n_taps};
 }
 
-// conv k5 s2 SAME: out grid = in / 2, taps (ky - 1, kx - 1) (TF pads 1 before, 2 after).
-int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, const float* bias,
-                float* out, uint32_t n, cudaStream_t st)
+// GDN / IGDN as a 1-tap contraction with the squared input (tfutils.py:393-397, 506-509). Pixel-wise,
+// hence indifferent to the storage order of the pixels: the plan is a flat [n_pixels, 128] matrix.
+int run_gdn(eae_codec* c, const float* in, float* out, uint32_t n_pixels, int which, bool inverse, cudaStream_t st)
+{
+    GemmPlan p = base_plan(in, 1, (int)n_pixels, 128, c->gamma[which].as<float>(), c->beta[which].as<float>(), out, 1);
+    p.mode = inverse ? kEpiIgdn : kEpiGdn;
+    return run_gemm(c, p, kLayerGdn, UmmaWeights{c->gk_hi[which].as<float>(), c->gk_lo[which].as<float>(), 1}, st);
+}
+
+// conv k5 s2 SAME: out grid = in / 2, taps (ky - 1, kx - 1) (TF pads 1 before, 2 after). The input is
+// stored parity-split (written so by its producer).
+int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, int layer, const float* bias,
+                float* out, bool out_split, uint32_t n, cudaStream_t st)
 {
     GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
     p.Hg = Hin / 2; p.Wg = Win / 2; p.in_mul = 2;
     p.Hout = p.Hg; p.Wout = p.Wg;
+    p.in_split = 1;
+    p.out_split = out_split ? 1 : 0;
     p.n_taps = 25;
     for (int ky = 0; ky < 5; ky++)
         for (int kx = 0; kx < 5; kx++)
             p.taps[ky * 5 + kx] = Tap{ky - 1, kx - 1, (uint32_t)(ky * 5 + kx) * 128u * 128u};
     p.M = n * (uint32_t)p.Hg * (uint32_t)p.Wg;
-    return run_gemm(c, p, 0, st);
+    return run_gemm(c, p, kLayerConv, umma_weights(c, layer, 25), st);
 }
 
 // conv2d_transpose k5 s2 SAME = 4 output phases; out[2a + r] gathers in[a + dy] through ky = r + 1 - 2 dy.
-int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, const float* bias,
+int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, int layer, const float* bias,
                  float* out, uint32_t n, cudaStream_t st)
 {
     for (int r = 0; r < 2; r++) {
@@ -214,7 +228,7 @@ int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w
                 }
             }
             p.n_taps = nt;
-            EAE_TRY(run_gemm(c, p, 0, st));
+            EAE_TRY(run_gemm(c, p, kLayerTconv, umma_weights(c, layer, 25), st));
         }
     }
     return 0;
@@ -227,19 +241,20 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     float* A = c->bufA.as<float>();
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
-    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction, then GDN
+    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction (output parity-split for the
+    // stride-2 layer that follows), then GDN in place
     { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
     {
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
-        EAE_TRY(run_gemm(c, p, -1, st));
+        p.out_split = 1;
+        EAE_TRY(run_gemm(c, p, kLayerThin, umma_weights(c, 0, 1), st));
     }
-    EAE_TRY(run_gdn(c, x1, x1, H1, W1, n, 0, false, st));
-    // layer 2
-    EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), c->bias[1].as<float>(), x2, n, st));
-    EAE_TRY(run_gdn(c, x2, x2, H2, W2, n, 1, false, st));
-    // layer 3
-    EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), c->bias[2].as<float>(), y_dev, n, st));
-    if (!c->learned) EAE_TRY(run_gdn(c, y_dev, y_dev, H3, W3, n, 2, false, st));
+    EAE_TRY(run_gdn(c, x1, x1, n * (uint32_t)(H1 * W1), 0, false, st));
+    // layer 2 (output parity-split again), layer 3 (natural NHWC: it is the latent the API returns)
+    EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), 1, c->bias[1].as<float>(), x2, true, n, st));
+    EAE_TRY(run_gdn(c, x2, x2, n * (uint32_t)(H2 * W2), 1, false, st));
+    EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), 2, c->bias[2].as<float>(), y_dev, false, n, st));
+    if (!c->learned) EAE_TRY(run_gdn(c, y_dev, y_dev, n * (uint32_t)(H3 * W3), 2, false, st));
     return 0;
 }
 
@@ -253,17 +268,17 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
     float* x3 = c->buf3.as<float>();
     const float* src = q_dev;
     if (!c->learned) {
-        EAE_TRY(run_gdn(c, q_dev, x3, H3, W3, n, 3, true, st));
+        EAE_TRY(run_gdn(c, q_dev, x3, n * (uint32_t)(H3 * W3), 3, true, st));
         src = x3;
     }
-    EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), c->bias[3].as<float>(), x2, n, st));
-    EAE_TRY(run_gdn(c, x2, x2, H2, W2, n, 4, true, st));
-    EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), c->bias[4].as<float>(), x1, n, st));
-    EAE_TRY(run_gdn(c, x1, x1, H1, W1, n, 5, true, st));
+    EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), 3, c->bias[3].as<float>(), x2, n, st));
+    EAE_TRY(run_gdn(c, x2, x2, n * (uint32_t)(H2 * W2), 4, true, st));
+    EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), 4, c->bias[4].as<float>(), x1, n, st));
+    EAE_TRY(run_gdn(c, x1, x1, n * (uint32_t)(H1 * W1), 5, true, st));
     // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias: per-pixel tap contributions, then col2im
     {
         GemmPlan p = base_plan(x1, H1, W1, 128, c->w6m.as<float>(), nullptr, P, n);
-        EAE_TRY(run_gemm(c, p, -1, st));
+        EAE_TRY(run_gemm(c, p, kLayerThin, umma_weights(c, 5, 1), st));
     }
     { ProfScope prof(kProfCol2im, st); EAE_TRY(launch_col2im_k9s4(P, out_u8_dev, out_f32_dev, n, (int)h, (int)w, st)); }
     return 0;
@@ -519,6 +534,44 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     }
     const float* biases[5] = {wt->biases_1, wt->biases_2, wt->biases_3, wt->biases_4, wt->biases_5};
     for (int i = 0; i < 5; i++) EAE_TRY(upload(c->bias[i], biases[i], 128));
+
+    // K-major, tf32-split copies for the tensor path: [taps][128 out][Cin]
+    {
+        std::vector<float> k;
+        // conv1: [128 out][96]  (TF [81][1][128 out] transposed, zero-padded)
+        k.assign((size_t)128 * kIm2colK, 0.f);
+        for (int t = 0; t < 81; t++)
+            for (int o = 0; o < 128; o++) k[(size_t)o * kIm2colK + t] = wt->weights_1[(size_t)t * 128 + o];
+        EAE_TRY(upload_split(c->wk_hi[0], c->wk_lo[0], k));
+        // conv2 / conv3: TF [tap][in][out] -> [tap][out][in]
+        const float* convs[2] = {wt->weights_2, wt->weights_3};
+        for (int l = 0; l < 2; l++) {
+            k.assign((size_t)25 * 128 * 128, 0.f);
+            for (int t = 0; t < 25; t++)
+                for (int i = 0; i < 128; i++)
+                    for (int o = 0; o < 128; o++)
+                        k[((size_t)t * 128 + o) * 128 + i] = convs[l][((size_t)t * 128 + i) * 128 + o];
+            EAE_TRY(upload_split(c->wk_hi[1 + l], c->wk_lo[1 + l], k));
+        }
+        // transposed convs: TF [tap][out][in] is already K-major
+        k.assign(wt->weights_4, wt->weights_4 + (size_t)25 * 128 * 128);
+        EAE_TRY(upload_split(c->wk_hi[3], c->wk_lo[3], k));
+        k.assign(wt->weights_5, wt->weights_5 + (size_t)25 * 128 * 128);
+        EAE_TRY(upload_split(c->wk_hi[4], c->wk_lo[4], k));
+        // tconv3: rows = the 81 filter taps (zero-padded to 128), K = 128 input channels: TF [81][1][128 in]
+        k.assign((size_t)128 * 128, 0.f);
+        memcpy(k.data(), wt->weights_6, (size_t)81 * 128 * 4);
+        EAE_TRY(upload_split(c->wk_hi[5], c->wk_lo[5], k));
+        // gamma[j in][i out] -> [i][j]
+        for (int g = 0; g < 6; g++) {
+            if (!gammas[g]) continue;
+            k.assign((size_t)128 * 128, 0.f);
+            for (int j = 0; j < 128; j++)
+                for (int i = 0; i < 128; i++) k[(size_t)i * 128 + j] = gammas[g][(size_t)j * 128 + i];
+            EAE_TRY(upload_split(c->gk_hi[g], c->gk_lo[g], k));
+        }
+    }
+    if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
     *out = c.release();
     return 0;
 }
@@ -593,6 +646,7 @@ extern "C" int eae_encode_host(eae_codec_t* c, const uint8_t* img, uint32_t n, u
     EAE_TRY(eae_encode_dev(c, di.as<uint8_t>(), n, h, w, dy.as<float>(), stream));
     EAE_CUDA_OK(cudaMemcpyAsync(y_out, dy.p, ny * 4, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
     return 0;
 }
 
@@ -611,6 +665,7 @@ extern "C" int eae_decode_host(eae_codec_t* c, const float* q, uint32_t n, uint3
     EAE_TRY(eae_decode_dev(c, dq.as<float>(), n, h, w, dr.as<uint8_t>(), stream));
     EAE_CUDA_OK(cudaMemcpyAsync(rec_out, dr.p, nout, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
     return 0;
 }
 
@@ -665,6 +720,7 @@ extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm,
     EAE_CUDA_OK(cudaMemcpyAsync(flag, c->flag.p, 8, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaMemcpyAsync(&hs, c->stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
     if (flag[0] & 1u) { set_error("The rounded array elements cannot be represented as 16-bit signed integers."); return EAE_ERR_INT16_RANGE; }
     if (flag[1]) { set_error("Error of type %u during the encoding.", flag[1]); return (int)flag[1]; }
     if (total > dcap) { set_error("container needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)cap); return EAE_ERR_ARGUMENT; }
@@ -711,6 +767,7 @@ extern "C" int eae_decompress_host(eae_codec_t* c, const eae_coding_params_t* pr
     EAE_CUDA_OK(cudaMemcpyAsync(herr.data(), c->err.p, n_streams * 4, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaMemcpyAsync(rec, c->img_u8.p, nout, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
     for (uint64_t s = 0; s < n_streams; s++)
         if (herr[s]) { set_error("Error of type %u during the decoding.", herr[s]); return (int)herr[s]; }
     return 0;

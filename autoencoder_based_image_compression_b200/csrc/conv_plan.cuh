@@ -10,6 +10,8 @@
 //   conv2d_transpose k5 s2 (:63-76)         : 4 launches (output phases r, s), in_mul 1, out_mul 2,
 //                                             taps ky = r + 1 - 2 dy in [0, 5)  (exact adjoint, SAME)
 //   GDN / IGDN (tfutils.py:363-397,480-509) : 1 tap, A = in^2, W = gamma[j, i], epilogue in (/ or *) sqrt(acc + beta)
+//   (activations that feed a stride-2 convolution are stored parity-split so that each of its taps is
+//    a dense box of one parity plane: see in_split / out_split)
 //   conv k9 s4, Cin = 1 (:119-123)          : 1 tap over the im2col matrix [pixels, 96] (81 used)
 //   conv2d_transpose k9 s4, Cout = 1 (:79-84): 1 tap, W = [128, 81 -> 128]; col2im kernel finishes it
 #pragma once
@@ -43,6 +45,8 @@ struct GemmPlan {
     int Hout, Wout;
     int out_mul, out_r, out_s;
     int mode;
+    int in_split;        // input stored parity-split: [n][(y&1)*2+(x&1)][Hin/2][Win/2][Cin]
+    int out_split;       // output stored parity-split: [n][(y&1)*2+(x&1)][Hout/2][Wout/2][128]
     int n_taps;
     uint32_t M;          // n * Hg * Wg
     Tap taps[kMaxTaps];

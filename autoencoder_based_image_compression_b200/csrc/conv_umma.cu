@@ -1,18 +1,471 @@
-// tcgen05 / TMEM / TMA tap-list GEMM (placeholder until the kernel lands).
+// Tensor-core path of the tap-list implicit GEMM (conv_plan.cuh) for sm_100a: tcgen05.mma kind::tf32
+// with the fp32 accumulator in TMEM, A (activation tile of one tap, 32 channels) and B (weight slice
+// of that tap) staged in shared memory by TMA in the canonical K-major SWIZZLE_128B layout, an
+// mbarrier ring between the TMA producer warp, the single MMA-issuing thread and the epilogue warps.
+//
+//   out tile  : 128 positions (tile_w x tile_h of the layer's position grid) x 128 output channels
+//   K loop    : taps x (Cin / 32); one stage = one (tap, 32-channel chunk): A 16 KB + B 16 KB
+//   A via TMA : 5-D tensor [C, W, H, plane, image]; the tap only shifts the box origin; rows/columns
+//               outside the image are zero-filled by TMA, which IS TensorFlow's SAME padding
+//   stride 2  : the producing layer writes its output parity-split ([image][y&1][x&1][y/2][x/2][C]),
+//               so a stride-2 tap is a dense box of one parity plane (no strided gather)
+//   exact3x   : 3xTF32. B is pre-split on the host (hi = rna_tf32(w), lo = rna_tf32(w - hi)); A is
+//               split on the fly by the epilogue warps (lo = a - trunc_tf32(a) written next to the
+//               TMA tile); D += A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation.
+//
+// Every wait is bounded (clock64 timeout -> error flag) so that a protocol bug cannot hang the GPU.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "conv_plan.cuh"
 #include "transforms.cuh"
 
 namespace eae {
 
-int umma_available()
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int kTileBytes = kTileM * 128;    // 16 KB: 128 rows x 128 bytes
+constexpr int kUmmaThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue / A split
+constexpr uint32_t kTmemCols = 128;
+constexpr long long kTimeoutCycles = 400ll * 1000 * 1000;   // ~0.2 s
+
+template <bool kExact> struct Cfg {
+    static constexpr int kStageBytes = kExact ? 4 * kTileBytes : 2 * kTileBytes;   // A [A_lo] B [B_lo]
+    static constexpr int kStages = kExact ? 3 : 6;
+    static constexpr int kOffAlo = kTileBytes;
+    static constexpr int kOffBhi = kExact ? 2 * kTileBytes : kTileBytes;
+    static constexpr int kOffBlo = 3 * kTileBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+struct UmmaTap { int plane, fy, fx, w_tap; };
+
+struct UmmaParams {
+    int n_taps, kchunks;
+    int tile_w, tile_h, tiles_x, tiles_y;
+    int Hg, Wg;
+    float* out;
+    const float* bias;
+    const float* xin;        // GDN / IGDN: the un-squared input, same flat [M,128] indexing as `out`
+    int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int mode;                // EpilogueMode
+    uint32_t* error_flag;
+    UmmaTap taps[kMaxTaps];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    set_error("the tcgen05 path is not built into this library yet");
-    return EAE_ERR_ARGUMENT;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: false (and the error flag set) if the phase does not complete in time.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t who)
+{
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > kTimeoutCycles) {
+            atomicOr(error_flag, 1u << who);
+            return false;
+        }
+    }
+    return true;
 }
 
-int launch_gemm_umma(const GemmPlan&, const float*, bool, cudaStream_t)
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4)
 {
-    return umma_available();
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor bit layout): start >> 4 in
+// [0,14), LBO in [16,30) (unused here: one swizzle atom along K), SBO = 1024 B (8 rows x 128 B) in
+// [32,46), version 1 in [46,48), layout SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32, D fp32, A/B K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor bit layout).
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <bool kExact>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+                 const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ UmmaParams p)
+{
+    using C = Cfg<kExact>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full = bars;                       // TMA bytes landed
+    uint64_t* split = bars + C::kStages;         // A_lo written (exact mode)
+    uint64_t* empty = bars + 2 * C::kStages;     // MMAs that read the stage have completed
+    uint64_t* acc_full = bars + 3 * C::kStages;  // accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int a0 = (trem / p.tiles_x) * p.tile_h, b0 = (trem % p.tiles_x) * p.tile_w;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::kStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_iters = p.n_taps * p.kchunks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; it++) {
+                const int s = it % C::kStages;
+                if (!mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1, p.error_flag, 0)) break;
+                const int t = it / p.kchunks, kc = it - t * p.kchunks;
+                const UmmaTap tap = p.taps[t];
+                uint8_t* st = smem + s * C::kStageBytes;
+                mbar_expect_tx(&full[s], kExact ? 3 * kTileBytes : 2 * kTileBytes);
+                tma_load_5d(st, &map_a, &full[s], kc * kChunkK, b0 + tap.fx, a0 + tap.fy, tap.plane, img);
+                tma_load_3d(st + C::kOffBhi, &map_b_hi, &full[s], kc * kChunkK, 0, tap.w_tap);
+                if (kExact) tma_load_3d(st + C::kOffBlo, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            bool ok = true;
+            for (int it = 0; it < n_iters && ok; it++) {
+                const int s = it % C::kStages;
+                ok = mbar_wait((kExact || p.mode != kEpiBias) ? &split[s] : &full[s], (it / C::kStages) & 1,
+                               p.error_flag, 1);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+                #pragma unroll
+                for (int k = 0; k < kChunkK / 8; k++) {
+                    const uint64_t a_hi = make_desc(st + k * 32);
+                    const uint64_t b_hi = make_desc(st + C::kOffBhi + k * 32);
+                    umma_tf32(tmem_base, a_hi, b_hi, (it | k) ? 1u : 0u);
+                    if (kExact) {
+                        umma_tf32(tmem_base, make_desc(st + C::kOffAlo + k * 32), b_hi, 1u);
+                        umma_tf32(tmem_base, a_hi, make_desc(st + C::kOffBlo + k * 32), 1u);
+                    }
+                }
+                umma_commit(&empty[s]);   // implies tcgen05.fence::before_thread_sync
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ===== warps 2..5: A split (exact mode), then the epilogue =====
+        const int et = threadIdx.x - 64;   // 0..127
+        bool ok = true;
+        if (kExact || p.mode != kEpiBias) {
+            for (int it = 0; it < n_iters && ok; it++) {
+                const int s = it % C::kStages;
+                ok = mbar_wait(&full[s], (it / C::kStages) & 1, p.error_flag, 2);
+                if (!ok) break;
+                float4* a = reinterpret_cast<float4*>(smem + s * C::kStageBytes);
+                float4* alo = reinterpret_cast<float4*>(smem + s * C::kStageBytes + C::kOffAlo);
+                #pragma unroll
+                for (int j = 0; j < kTileBytes / 16 / 128; j++) {
+                    float4 v = a[et + 128 * j];
+                    if (p.mode != kEpiBias) {      // GDN / IGDN contract the squared input
+                        v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w;
+                        a[et + 128 * j] = v;
+                    }
+                    if (kExact) {
+                        float4 l;
+                        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        alo[et + 128 * j] = l;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor core reads
+                mbar_arrive(&split[s]);
+            }
+        }
+        if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // TMEM lane quarter of this warp is (warp % 4); accumulator row = TMEM lane.
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int a = a0 + row / p.tile_w, b = b0 + row % p.tile_w;
+        const bool valid = ok && a < p.Hg && b < p.Wg;
+        size_t opix = 0;
+        if (valid) {
+            const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
+            if (p.out_split)
+                opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
+            else
+                opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+        }
+        float* o = p.out + opix * kCout;
+        const float* xi = p.xin + opix * kCout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        #pragma unroll 1
+        for (int c0 = 0; c0 < kCout; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            if (valid) {
+                #pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (p.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                        r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                    }
+                    if (p.mode != kEpiBias) {
+                        const float4 x = *reinterpret_cast<const float4*>(xi + c0 + j);
+                        if (p.mode == kEpiGdn) {
+                            r.x = __fdiv_rn(x.x, __fsqrt_rn(r.x)); r.y = __fdiv_rn(x.y, __fsqrt_rn(r.y));
+                            r.z = __fdiv_rn(x.z, __fsqrt_rn(r.z)); r.w = __fdiv_rn(x.w, __fsqrt_rn(r.w));
+                        } else {
+                            r.x = __fmul_rn(x.x, __fsqrt_rn(r.x)); r.y = __fmul_rn(x.y, __fsqrt_rn(r.y));
+                            r.z = __fmul_rn(x.z, __fsqrt_rn(r.z)); r.w = __fmul_rn(x.w, __fsqrt_rn(r.w));
+                        }
+                    }
+                    *reinterpret_cast<float4*>(o + c0 + j) = r;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EAE_ERR_CUDA; }
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bdim[5], estride[5];
+    uint64_t stride = sizeof(float);
+    for (int i = 0; i < rank; i++) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estride[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim,
+                    estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return EAE_ERR_CUDA; }
+    return 0;
+}
+
+uint32_t* g_error_flag = nullptr;   // device word, per process (one device per process in practice)
+
+}  // namespace
+
+int umma_available()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return EAE_ERR_CUDA; }
+    cudaDeviceProp prop;
+    EAE_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error("the tcgen05 path needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
+        return EAE_ERR_CUDA;
+    }
+    if (!encode_tiled_fn()) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EAE_ERR_CUDA; }
+    return 0;
+}
+
+int umma_check_error(cudaStream_t st)
+{
+    if (!g_error_flag) return 0;
+    uint32_t flag = 0;
+    EAE_CUDA_OK(cudaMemcpyAsync(&flag, g_error_flag, 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (flag) {
+        cudaMemsetAsync(g_error_flag, 0, 4, st);
+        set_error("tcgen05 GEMM pipeline timed out (role mask 0x%x)", flag);
+        return EAE_ERR_CUDA;
+    }
+    return 0;
+}
+
+int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, bool exact3x, cudaStream_t st)
+{
+    if (plan.M == 0) return 0;
+    if (plan.Cin % kChunkK != 0 || plan.n_taps < 1 || plan.n_taps > kMaxTaps || !w.hi || (exact3x && !w.lo)) {
+        set_error("gemm_umma: bad plan (Cin %d, taps %d)", plan.Cin, plan.n_taps);
+        return EAE_ERR_ARGUMENT;
+    }
+    if (!g_error_flag) {
+        EAE_CUDA_OK(cudaMalloc(&g_error_flag, 4));
+        EAE_CUDA_OK(cudaMemset(g_error_flag, 0, 4));
+    }
+    const uint32_t per_img = (uint32_t)(plan.Hg * plan.Wg);
+    const uint32_t n_img = plan.M / per_img;
+    UmmaParams p;
+    memset(&p, 0, sizeof p);
+    p.n_taps = plan.n_taps;
+    p.kchunks = plan.Cin / kChunkK;
+    // Position grids that are wide enough use 16 x 8 tiles; flat (1-row) grids use 128 x 1.
+    if (plan.Hg == 1) { p.tile_w = 128; p.tile_h = 1; } else { p.tile_w = 16; p.tile_h = 8; }
+    p.tiles_x = (plan.Wg + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (plan.Hg + p.tile_h - 1) / p.tile_h;
+    p.Hg = plan.Hg; p.Wg = plan.Wg;
+    p.out = plan.out; p.bias = plan.bias; p.xin = plan.in;
+    p.Hout = plan.Hout; p.Wout = plan.Wout; p.out_mul = plan.out_mul; p.out_r = plan.out_r; p.out_s = plan.out_s;
+    p.out_split = plan.out_split;
+    p.mode = plan.mode;
+    p.error_flag = g_error_flag;
+    // Input planes: natural NHWC (1 plane) or parity-split (4 planes of Hin/2 x Win/2).
+    const int planes = plan.in_split ? 4 : 1;
+    const int Hp = plan.in_split ? plan.Hin / 2 : plan.Hin, Wp = plan.in_split ? plan.Win / 2 : plan.Win;
+    for (int t = 0; t < plan.n_taps; t++) {
+        const int dy = plan.taps[t].dy, dx = plan.taps[t].dx;
+        UmmaTap& u = p.taps[t];
+        if (plan.in_split) {
+            if (plan.in_mul != 2) { set_error("gemm_umma: split input needs in_mul 2"); return EAE_ERR_ARGUMENT; }
+            u.plane = (dy & 1) * 2 + (dx & 1);
+            u.fy = (dy - (dy & 1)) / 2;      // floor(dy / 2)
+            u.fx = (dx - (dx & 1)) / 2;
+        } else {
+            if (plan.in_mul != 1) { set_error("gemm_umma: natural input needs in_mul 1"); return EAE_ERR_ARGUMENT; }
+            u.plane = 0; u.fy = dy; u.fx = dx;
+        }
+        u.w_tap = (int)(plan.taps[t].w_off / ((uint32_t)plan.Cin * kCout));
+    }
+    CUtensorMap map_a, map_b_hi, map_b_lo;
+    const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
+    const uint32_t abox[5] = {kChunkK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
+    EAE_TRY(make_map(&map_a, plan.in, 5, adims, abox));
+    const uint64_t bdims[3] = {(uint64_t)plan.Cin, kCout, (uint64_t)w.n_taps};
+    const uint32_t bbox[3] = {kChunkK, kCout, 1};
+    EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
+    EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
+    const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
+    if (exact3x) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg<true>::kSmemBytes));
+            attr_done = true;
+        }
+        gemm_umma_kernel<true><<<grid, kUmmaThreads, Cfg<true>::kSmemBytes, st>>>(map_a, map_b_hi, map_b_lo, p);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg<false>::kSmemBytes));
+            attr_done = true;
+        }
+        gemm_umma_kernel<false><<<grid, kUmmaThreads, Cfg<false>::kSmemBytes, st>>>(map_a, map_b_hi, map_b_lo, p);
+    }
+    EAE_LAUNCH_OK();
+    return 0;
 }
 
 }  // namespace eae

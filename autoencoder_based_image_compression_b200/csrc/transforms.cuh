@@ -12,7 +12,16 @@ constexpr int kIm2colK = 96;  // 81 taps of the 9x9 kernel, zero-padded to a mul
 int launch_gemm_simt(const GemmPlan& plan, cudaStream_t st);
 // tcgen05 / TMEM / TMA tap-list GEMM; exact3x = hi/lo split of both operands (3 MMAs per product).
 // w_lo: the low parts of the weights, same layout as plan.w (only read when exact3x).
-int launch_gemm_umma(const GemmPlan& plan, const float* w_lo, bool exact3x, cudaStream_t st);
+// Weights of one layer for the tensor path: K-major [taps][128 out][Cin], tf32-rounded high part and
+// (for exact3x) the tf32-rounded remainder.
+struct UmmaWeights {
+    const float* hi;
+    const float* lo;
+    int n_taps;
+};
+int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, bool exact3x, cudaStream_t st);
+// Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
+int umma_check_error(cudaStream_t st);
 // 0 if the tcgen05 path can run on the current device (sm_100), else an error code with message.
 int umma_available();
 

@@ -58,8 +58,15 @@ gemm_simt_kernel(const __grid_constant__ GemmPlan p)
             const int iy = iy0[r] + tap.dy, ix = ix0[r] + tap.dx;
             const bool ok = row_ok[r] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v = __ldg(reinterpret_cast<const float4*>(
-                            p.in + (img_off[r] + (size_t)iy * p.Win + ix) * p.Cin + c0 + a_c4 * 4));
+            if (ok) {
+                size_t pix;
+                if (p.in_split)   // img_off is a multiple of Hin * Win = 4 planes of (Hin/2) * (Win/2)
+                    pix = img_off[r] + ((size_t)((iy & 1) * 2 + (ix & 1)) * (size_t)(p.Hin / 2) + (size_t)(iy >> 1)) *
+                                           (size_t)(p.Win / 2) + (size_t)(ix >> 1);
+                else
+                    pix = img_off[r] + (size_t)iy * p.Win + ix;
+                v = __ldg(reinterpret_cast<const float4*>(p.in + pix * p.Cin + c0 + a_c4 * 4));
+            }
             if (p.mode != kEpiBias) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
             ra[r] = v;
             rb[r] = __ldg(reinterpret_cast<const float4*>(
@@ -122,8 +129,11 @@ gemm_simt_kernel(const __grid_constant__ GemmPlan p)
         if (m >= p.M) continue;
         const uint32_t img = m / per_img, rem = m % per_img;
         const int a = (int)(rem / p.Wg), b = (int)(rem % p.Wg);
-        const size_t opix = ((size_t)img * p.Hout + (size_t)(a * p.out_mul + p.out_r)) * p.Wout +
-                            (size_t)(b * p.out_mul + p.out_s);
+        const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
+        const size_t opix = p.out_split
+            ? (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (size_t)(p.Hout / 2) + (size_t)(oy >> 1)) *
+                  (size_t)(p.Wout / 2) + (size_t)(ox >> 1)
+            : ((size_t)img * p.Hout + (size_t)oy) * p.Wout + (size_t)ox;
         float4 v0 = make_float4(acc[i][0] + bias0.x, acc[i][1] + bias0.y, acc[i][2] + bias0.z, acc[i][3] + bias0.w);
         float4 v1 = make_float4(acc[i][4] + bias1.x, acc[i][5] + bias1.y, acc[i][6] + bias1.z, acc[i][7] + bias1.w);
         if (p.mode != kEpiBias) {
