@@ -109,6 +109,7 @@ PROTOTYPES = {
     'eae_encode_dev': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
     'eae_decode_host': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
     'eae_decode_dev': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
+    'eae_decode_float_host': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
     'eae_container_bound': (u64, [u32, u32, u32, u32]),
     'eae_compress_host': (c_int, [c_void_p, P(CodingParams), c_void_p, u32, u32, u32, c_void_p, u64, P(u64),
                                   P(BatchStats), c_void_p]),

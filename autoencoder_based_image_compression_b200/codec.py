@@ -123,6 +123,15 @@ class Codec(object):
         _native.check(_native.lib().eae_decode_host(self.handle, _native.ptr(q), n, h, w, _native.ptr(out), None))
         return out
 
+    def decode_float(self, quantized_y_float32):
+        """The decoder's float32 output ``node_reconstruction`` before ``cast_bt601`` (components.py:79-84)."""
+        q = numpy.ascontiguousarray(quantized_y_float32, dtype=numpy.float32)
+        (n, hl, wl, _) = q.shape
+        out = numpy.empty((n, hl*16, wl*16, 1), dtype=numpy.float32)
+        _native.check(_native.lib().eae_decode_float_host(self.handle, _native.ptr(q), n, hl*16, wl*16,
+                                                          _native.ptr(out), None))
+        return out
+
     # ---- fused pipeline ----
     def compress(self, luminances_uint8, params, container=None, return_stats=False):
         """uint8 [n, h, w] -> container bytes (numpy uint8 view). See include/eae_b200.h for the layout."""

@@ -669,6 +669,30 @@ extern "C" int eae_decode_host(eae_codec_t* c, const float* q, uint32_t n, uint3
     return 0;
 }
 
+extern "C" int eae_decode_float_host(eae_codec_t* c, const float* q, uint32_t n, uint32_t h, uint32_t w,
+                                     float* rec_out, void* stream)
+{
+    if (!c || !q || !rec_out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(check_dims(n, h, w));
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf dq, dr;
+    const size_t nout = (size_t)n * h * w, per_q = (size_t)(h / 16) * (w / 16) * 128;
+    EAE_TRY(dq.alloc((size_t)n * per_q * 4));
+    EAE_TRY(dr.alloc(nout * 4));
+    EAE_CUDA_OK(cudaMemcpyAsync(dq.p, q, (size_t)n * per_q * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t chunk = chunk_images(h, w);
+    EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
+    for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
+        const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
+        EAE_TRY(decode_chunk(c, dq.as<float>() + i0 * per_q, nc, h, w, nullptr, dr.as<float>() + (size_t)i0 * h * w, st));
+    }
+    EAE_CUDA_OK(cudaMemcpyAsync(rec_out, dr.p, nout * 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
+    return 0;
+}
+
 extern "C" uint64_t eae_container_bound(uint32_t n, uint32_t h, uint32_t w, uint32_t L)
 {
     const uint64_t size = (uint64_t)(h / 16) * (w / 16);

@@ -269,6 +269,10 @@ int eae_decode_host(eae_codec_t* codec, const float* quantized_y, uint32_t n, ui
                     uint8_t* reconstruction_out, void* stream);
 int eae_decode_dev(eae_codec_t* codec, const float* quantized_y_dev, uint32_t n, uint32_t h, uint32_t w,
                    uint8_t* reconstruction_out_dev, void* stream);
+/* The decoder graph's float32 output node_reconstruction itself (components.py:79-84), before
+ * tls.cast_bt601: float32 [n, h/16, w/16, 128] -> float32 [n, h, w, 1]. */
+int eae_decode_float_host(eae_codec_t* codec, const float* quantized_y, uint32_t n, uint32_t h, uint32_t w,
+                          float* reconstruction_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Fused codec: encode -> quantize -> lossless code -> container, and back                     */

@@ -11,6 +11,7 @@ from oracle import coder as oracle_coder
 from oracle import glue as oracle_glue
 from oracle import transforms as T
 from tests import util
+from tests.test_gpu_transforms import PARITY_MODES, visible_weights
 
 pytestmark = pytest.mark.gpu
 
@@ -26,16 +27,17 @@ def oracle_pipeline(lum, w, learned, params):
     return (y, idx, rec)
 
 
+@pytest.mark.parametrize('math', PARITY_MODES)
 @pytest.mark.parametrize('learned', [False, True])
-def test_round_trip_and_byte_identity(native, golden, learned):
+def test_round_trip_and_byte_identity(native, golden, learned, math):
     rng = numpy.random.default_rng(3)
-    w = wts.random_init(0, learned)
+    w = visible_weights(0, learned)
     (n, h, wd) = (3, 128, 192)
     lum = util.synthetic_luma(rng, n, h, wd)
     model = 'learning_bw_0dot5_10000' if learned else '1_10000'
     params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table(model, '1'),
                                        0.05*golden.map_mean(model))
-    codec = native_codec.Codec(w, learned)
+    codec = native_codec.Codec(w, learned, math=math)
     (blob, stats) = codec.compress(lum, params, return_stats=True)
     idx_gpu = codec.last_indices(n, h, wd)                       # [n, 128, hw]
     (info, streams) = native_codec.parse_container(blob)
@@ -75,12 +77,13 @@ def test_round_trip_and_byte_identity(native, golden, learned):
     assert abs(total - bits_ref) <= 1e-3*bits_ref
 
 
-def test_quantization_sweep(native, golden):
+@pytest.mark.parametrize('math', PARITY_MODES)
+def test_quantization_sweep(native, golden, math):
     """BASELINE config 3 at test scale: one EAE, bin widths delta x {1, 2, 4, 8}."""
     rng = numpy.random.default_rng(4)
-    w = wts.random_init(0, False)
+    w = visible_weights(0, False)
     lum = util.synthetic_luma(rng, 2, 128, 128)
-    codec = native_codec.Codec(w, False)
+    codec = native_codec.Codec(w, False, math=math)
     rates = []
     psnrs = []
     for mult in (1, 2, 4, 8):

@@ -2,7 +2,9 @@
 through the reference-facing API (EntropyAutoencoder / IsolatedDecoder / eae.batching).
 
 Tolerances (BASELINE.json north_star): quantization indices agree on >= 99.99 % of the coefficients
-and every mismatch sits next to a bin boundary; reconstruction PSNR within 0.01 dB."""
+and every mismatch sits next to a bin boundary; reconstruction PSNR within 0.01 dB. Checked for the
+fp32 CUDA-core path ('fp32') and the 3xTF32 tensor-core path ('tf32x3'); the single-pass TF32 mode is a
+throughput mode whose mismatch rate is measured and bounded, not held to the parity bar."""
 import numpy
 import pytest
 import torch
@@ -18,7 +20,7 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 
-MATH_MODES = ['fp32']
+PARITY_MODES = ['fp32', 'tf32x3']
 
 
 def index_agreement(y_gpu, y_ref64, delta=1.0):
@@ -32,11 +34,21 @@ def index_agreement(y_gpu, y_ref64, delta=1.0):
     return (frac, worst, int(diff.sum()))
 
 
-@pytest.mark.parametrize('math', MATH_MODES)
+def visible_weights(seed, learned):
+    """Random-init weights whose reconstructions land inside the BT.601 range instead of being clipped
+    to 16: a positive bias before the last IGDN and a larger last filter (the reference's initial
+    distributions give a zero-mean output, see EntropyAutoencoder.py:131-224)."""
+    w = wts.random_init(seed, learned)
+    w['decoder/biases_5'] = (w['decoder/biases_5'] + 2.0).astype(numpy.float32)
+    w['decoder/weights_6'] = (numpy.abs(w['decoder/weights_6'])*8.).astype(numpy.float32)
+    return w
+
+
+@pytest.mark.parametrize('math', PARITY_MODES)
 @pytest.mark.parametrize('learned', [False, True])
 def test_encoder_decoder_small(native, learned, math):
     rng = numpy.random.default_rng(0)
-    w = wts.random_init(0, learned)
+    w = visible_weights(0, learned)
     (n, h, wd) = (4, 64, 96)
     lum = util.synthetic_luma(rng, n, h, wd, smooth=False)[..., None]
     sess = native_codec.Session(0, math=math)
@@ -47,17 +59,21 @@ def test_encoder_decoder_small(native, learned, math):
     y32 = T.encoder(lum.astype(numpy.float32), w, learned)
     y64 = T.encoder(lum.astype(numpy.float64), w, learned, dtype=torch.float64)
     scale = numpy.abs(y64).max()
-    assert numpy.abs(y - y64).max() <= 4.*max(numpy.abs(y32 - y64).max(), 1e-6*scale)
+    assert numpy.abs(y - y64).max() <= 5e-5*scale, numpy.abs(y - y64).max()/scale
     (frac, worst, nb) = index_agreement(y, y64)
     assert frac >= 0.9999 and worst < 1e-4, (frac, worst, nb)
-    # decoder on the oracle's quantized latent
+    # decoder on the oracle's quantized latent: float output, then the uint8 cast
     q = oracle_glue.quantize_per_map(y32, numpy.ones(128, dtype=numpy.float32))
     dec = IsolatedDecoder(4, h, wd, learned)
     dec.set_weights(w)
+    rec64 = T.decoder(q.astype(numpy.float64), w, learned, dtype=torch.float64)
+    rec_f = dec.codec(sess).decode_float(q)
+    assert rec_f.shape == (n, h, wd, 1)
+    assert numpy.abs(rec_f - rec64).max() <= 5e-5*numpy.abs(rec64).max(), numpy.abs(rec_f - rec64).max()
     rec = batching.decode_mini_batches(q, sess, dec, 4)
     assert rec.shape == (n, h, wd, 1) and rec.dtype == numpy.uint8
-    rec64 = T.decoder(q.astype(numpy.float64), w, learned, dtype=torch.float64)
     want = oracle_glue.cast_bt601(rec64)
+    assert 20 < want.mean() < 230 and want.std() > 5      # the test really exercises un-clipped pixels
     delta = numpy.abs(rec.astype(numpy.int32) - want.astype(numpy.int32))
     assert delta.max() <= 1 and (delta != 0).mean() < 1e-3
     assert rec.min() >= 16 and rec.max() <= 235
@@ -72,12 +88,13 @@ def test_all_zero_latent_gives_constant_reconstruction(native):
     assert rec.min() == rec.max() == 16     # reconstruction 0.0 clipped to the BT.601 floor
 
 
-def test_kodak_size_image_against_oracle(native):
+@pytest.mark.parametrize('math', PARITY_MODES)
+def test_kodak_size_image_against_oracle(native, math):
     """BASELINE config 1: one 512 x 768 image, delta = 1, fixed-delta variant (6 GDN/IGDN)."""
     rng = numpy.random.default_rng(1)
-    w = wts.random_init(0, False)
+    w = visible_weights(0, False)
     lum = util.synthetic_luma(rng, 1, 512, 768)[..., None]
-    codec = native_codec.Codec(w, False)
+    codec = native_codec.Codec(w, False, math=math)
     y = codec.encode(lum)
     y64 = T.encoder(lum.astype(numpy.float64), w, False, dtype=torch.float64)
     y32 = T.encoder(lum.astype(numpy.float32), w, False)
@@ -87,17 +104,19 @@ def test_kodak_size_image_against_oracle(native):
     q = oracle_glue.quantize_per_map(y32, numpy.ones(128, dtype=numpy.float32))
     rec = codec.decode(q)[..., 0]
     want = oracle_glue.cast_bt601(T.decoder(q, w, False))[..., 0]
+    assert want.std() > 5
     psnr_gpu = oracle_glue.psnr_2d(lum[0, :, :, 0], rec[0])
     psnr_ref = oracle_glue.psnr_2d(lum[0, :, :, 0], want[0])
     assert abs(psnr_gpu - psnr_ref) < 0.01
     assert (rec != want).mean() < 1e-3
 
 
-def test_non_multiple_tile_sizes_and_4k_frame_shape(native):
-    """Latent grids that are not multiples of the 128-row GEMM tile, incl. the 4K frame (135 x 240)."""
+@pytest.mark.parametrize('math', PARITY_MODES)
+def test_non_multiple_tile_sizes_and_4k_frame_shape(native, math):
+    """Latent grids that are not multiples of the GEMM tile, incl. the 4K frame (135 x 240 latent)."""
     rng = numpy.random.default_rng(2)
-    w = wts.random_init(2, True)
-    codec = native_codec.Codec(w, True)
+    w = visible_weights(2, True)
+    codec = native_codec.Codec(w, True, math=math)
     for (h, wd) in ((16, 16), (48, 80), (2160, 3840)):
         lum = util.synthetic_luma(rng, 1, h, wd)[..., None]
         y = codec.encode(lum)
@@ -106,6 +125,22 @@ def test_non_multiple_tile_sizes_and_4k_frame_shape(native):
         tol = 2e-4*max(1., numpy.abs(y32).max())
         assert numpy.abs(y - y32).max() < tol
         q = numpy.round(y32)
+        rec_f = codec.decode_float(q)
+        want_f = T.decoder(q, w, True)
+        assert numpy.abs(rec_f - want_f).max() < 2e-4*numpy.abs(want_f).max()
         rec = codec.decode(q)
-        want = oracle_glue.cast_bt601(T.decoder(q, w, True))
-        assert (rec != want).mean() < 1e-3
+        assert (rec != oracle_glue.cast_bt601(want_f)).mean() < 1e-3
+
+
+def test_single_pass_tf32_is_close_but_not_exact(native):
+    """The throughput mode: measured against the fp64 oracle, bounded, and reported (not hidden)."""
+    rng = numpy.random.default_rng(3)
+    w = visible_weights(0, False)
+    lum = util.synthetic_luma(rng, 2, 128, 192)[..., None]
+    codec = native_codec.Codec(w, False, math='tf32')
+    y = codec.encode(lum)
+    y64 = T.encoder(lum.astype(numpy.float64), w, False, dtype=torch.float64)
+    (frac, _, nb) = index_agreement(y, y64)
+    print('single-pass TF32: index agreement {:.6f} ({} mismatches of {})'.format(frac, nb, y.size))
+    assert frac > 0.995
+    assert numpy.abs(y - y64).max() < 5e-3*numpy.abs(y64).max()
