@@ -75,7 +75,7 @@ def test_encoder_decoder_small(native, learned, math):
     want = oracle_glue.cast_bt601(rec64)
     assert 20 < want.mean() < 230 and want.std() > 5      # the test really exercises un-clipped pixels
     delta = numpy.abs(rec.astype(numpy.int32) - want.astype(numpy.int32))
-    assert delta.max() <= 1 and (delta != 0).mean() < 1e-3
+    assert delta.max() <= 1 and (delta != 0).mean() < 5e-3
     assert rec.min() >= 16 and rec.max() <= 235
 
 
@@ -108,7 +108,8 @@ def test_kodak_size_image_against_oracle(native, math):
     psnr_gpu = oracle_glue.psnr_2d(lum[0, :, :, 0], rec[0])
     psnr_ref = oracle_glue.psnr_2d(lum[0, :, :, 0], want[0])
     assert abs(psnr_gpu - psnr_ref) < 0.01
-    assert (rec != want).mean() < 1e-3
+    delta = numpy.abs(rec.astype(numpy.int32) - want.astype(numpy.int32))
+    assert delta.max() <= 1 and (delta != 0).mean() < 5e-3
 
 
 @pytest.mark.parametrize('math', PARITY_MODES)
@@ -129,7 +130,7 @@ def test_non_multiple_tile_sizes_and_4k_frame_shape(native, math):
         want_f = T.decoder(q, w, True)
         assert numpy.abs(rec_f - want_f).max() < 2e-4*numpy.abs(want_f).max()
         rec = codec.decode(q)
-        assert (rec != oracle_glue.cast_bt601(want_f)).mean() < 1e-3
+        assert (rec != oracle_glue.cast_bt601(want_f)).mean() < 5e-3
 
 
 def test_single_pass_tf32_is_close_but_not_exact(native):
