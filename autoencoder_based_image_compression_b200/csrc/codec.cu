@@ -18,6 +18,7 @@ struct eae_codec {
     int learned = 0;   // are_bin_widths_learned: 4 GDN/IGDN instead of 6
     int math = EAE_MATH_FP32_SIMT;
     int umma_mask = 0xF;   // which layer kinds run on tensor cores (debug: env EAE_UMMA_LAYERS)
+    int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
     cudaStream_t own_stream = nullptr;
 
     // ---- weights (device) ----
@@ -151,7 +152,8 @@ int check_dims(uint32_t n, uint32_t h, uint32_t w)
 // ---- layer launchers --------------------------------------------------------------------------
 enum LayerKind : int { kLayerConv = 0, kLayerTconv = 1, kLayerGdn = 2, kLayerThin = 3 };
 
-int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw, cudaStream_t st)
+int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw, const UmmaWeights* gamma,
+             cudaStream_t st)
 {
     static const int prof_of_kind[4] = {kProfGemmConv, kProfGemmTconv, kProfGemmGdn, kProfGemmThin};
     ProfScope prof(prof_of_kind[kind], st);
@@ -159,7 +161,14 @@ int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw
     // GDN / IGDN always use the split contraction: a single-pass TF32 norm would put a 2^-12 relative
     // error on every activation, for 4 % of the FLOPs.
     const bool exact = c->math == EAE_MATH_TF32X3 || kind == kLayerGdn;
-    return launch_gemm_umma(plan, uw, exact, st);
+    return launch_gemm_umma(plan, uw, gamma, exact, st);
+}
+
+// Can the GDN / IGDN that follows a contraction of this kind run inside its epilogue?
+bool can_fuse(const eae_codec* c, int kind)
+{
+    return c->math != EAE_MATH_FP32_SIMT && umma_version() == 2 && ((c->umma_mask >> kind) & 1) &&
+           ((c->umma_mask >> kLayerGdn) & 1) && !c->no_fuse;
 }
 
 GemmPlan base_plan(const float* in, int Hin, int Win, int Cin, const float* w, const float* bias, float* out,
@@ -188,13 +197,28 @@ int run_gdn(eae_codec* c, const float* in, float* out, uint32_t n_pixels, int wh
 {
     GemmPlan p = base_plan(in, 1, (int)n_pixels, 128, c->gamma[which].as<float>(), c->beta[which].as<float>(), out, 1);
     p.mode = inverse ? kEpiIgdn : kEpiGdn;
-    return run_gemm(c, p, kLayerGdn, UmmaWeights{c->gk_hi[which].as<float>(), c->gk_lo[which].as<float>(), 1}, st);
+    return run_gemm(c, p, kLayerGdn, UmmaWeights{c->gk_hi[which].as<float>(), c->gk_lo[which].as<float>(), 1}, nullptr, st);
+}
+
+// One contraction followed by GDN / IGDN number `gdn` (-1: none): inside the epilogue on the tensor path,
+// as a second launch otherwise. `plans` are the launches that together produce `out_pixels` pixels at out.
+int run_layer(eae_codec* c, GemmPlan* plans, int n_plans, int kind, const UmmaWeights& uw, int gdn, bool inverse,
+              uint32_t out_pixels, cudaStream_t st)
+{
+    const bool fuse = gdn >= 0 && can_fuse(c, kind);
+    const UmmaWeights gw{gdn >= 0 ? c->gk_hi[gdn].as<float>() : nullptr, gdn >= 0 ? c->gk_lo[gdn].as<float>() : nullptr, 1};
+    for (int i = 0; i < n_plans; i++) {
+        if (fuse) { plans[i].fuse = inverse ? 2 : 1; plans[i].fuse_beta = c->beta[gdn].as<float>(); }
+        EAE_TRY(run_gemm(c, plans[i], kind, uw, fuse ? &gw : nullptr, st));
+    }
+    if (gdn >= 0 && !fuse) EAE_TRY(run_gdn(c, plans[0].out, plans[0].out, out_pixels, gdn, inverse, st));
+    return 0;
 }
 
 // conv k5 s2 SAME: out grid = in / 2, taps (ky - 1, kx - 1) (TF pads 1 before, 2 after). The input is
 // stored parity-split (written so by its producer).
 int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, int layer, const float* bias,
-                float* out, bool out_split, uint32_t n, cudaStream_t st)
+                float* out, bool out_split, int gdn, uint32_t n, cudaStream_t st)
 {
     GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
     p.Hg = Hin / 2; p.Wg = Win / 2; p.in_mul = 2;
@@ -206,16 +230,18 @@ int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w,
         for (int kx = 0; kx < 5; kx++)
             p.taps[ky * 5 + kx] = Tap{ky - 1, kx - 1, (uint32_t)(ky * 5 + kx) * 128u * 128u};
     p.M = n * (uint32_t)p.Hg * (uint32_t)p.Wg;
-    return run_gemm(c, p, kLayerConv, umma_weights(c, layer, 25), st);
+    return run_layer(c, &p, 1, kLayerConv, umma_weights(c, layer, 25), gdn, false, p.M, st);
 }
 
 // conv2d_transpose k5 s2 SAME = 4 output phases; out[2a + r] gathers in[a + dy] through ky = r + 1 - 2 dy.
 int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, int layer, const float* bias,
-                 float* out, uint32_t n, cudaStream_t st)
+                 float* out, int gdn, uint32_t n, cudaStream_t st)
 {
+    GemmPlan plans[4];
     for (int r = 0; r < 2; r++) {
         for (int s = 0; s < 2; s++) {
-            GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
+            GemmPlan& p = plans[r * 2 + s];
+            p = base_plan(in, Hin, Win, 128, w, bias, out, n);
             p.Hout = 2 * Hin; p.Wout = 2 * Win; p.out_mul = 2; p.out_r = r; p.out_s = s;
             int nt = 0;
             for (int ky = 0; ky < 5; ky++) {
@@ -228,33 +254,30 @@ int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w
                 }
             }
             p.n_taps = nt;
-            EAE_TRY(run_gemm(c, p, kLayerTconv, umma_weights(c, layer, 25), st));
         }
     }
-    return 0;
+    return run_layer(c, plans, 4, kLayerTconv, umma_weights(c, layer, 25), gdn, true, 4 * plans[0].M, st);
 }
 
 int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, uint32_t w, float* y_dev,
                  cudaStream_t st)
 {
-    const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8, H3 = h / 16, W3 = w / 16;
+    const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8;
     float* A = c->bufA.as<float>();
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
-    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction (output parity-split for the
-    // stride-2 layer that follows), then GDN in place
+    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction, GDN; output parity-split for the
+    // stride-2 layer that follows
     { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
     {
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
         p.out_split = 1;
-        EAE_TRY(run_gemm(c, p, kLayerThin, umma_weights(c, 0, 1), st));
+        EAE_TRY(run_layer(c, &p, 1, kLayerThin, umma_weights(c, 0, 1), 0, false, p.M, st));
     }
-    EAE_TRY(run_gdn(c, x1, x1, n * (uint32_t)(H1 * W1), 0, false, st));
     // layer 2 (output parity-split again), layer 3 (natural NHWC: it is the latent the API returns)
-    EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), 1, c->bias[1].as<float>(), x2, true, n, st));
-    EAE_TRY(run_gdn(c, x2, x2, n * (uint32_t)(H2 * W2), 1, false, st));
-    EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), 2, c->bias[2].as<float>(), y_dev, false, n, st));
-    if (!c->learned) EAE_TRY(run_gdn(c, y_dev, y_dev, n * (uint32_t)(H3 * W3), 2, false, st));
+    EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), 1, c->bias[1].as<float>(), x2, true, 1, n, st));
+    EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), 2, c->bias[2].as<float>(), y_dev, false,
+                        c->learned ? -1 : 2, n, st));
     return 0;
 }
 
@@ -271,14 +294,12 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
         EAE_TRY(run_gdn(c, q_dev, x3, n * (uint32_t)(H3 * W3), 3, true, st));
         src = x3;
     }
-    EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), 3, c->bias[3].as<float>(), x2, n, st));
-    EAE_TRY(run_gdn(c, x2, x2, n * (uint32_t)(H2 * W2), 4, true, st));
-    EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), 4, c->bias[4].as<float>(), x1, n, st));
-    EAE_TRY(run_gdn(c, x1, x1, n * (uint32_t)(H1 * W1), 5, true, st));
+    EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), 3, c->bias[3].as<float>(), x2, 4, n, st));
+    EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), 4, c->bias[4].as<float>(), x1, 5, n, st));
     // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias: per-pixel tap contributions, then col2im
     {
         GemmPlan p = base_plan(x1, H1, W1, 128, c->w6m.as<float>(), nullptr, P, n);
-        EAE_TRY(run_gemm(c, p, kLayerThin, umma_weights(c, 5, 1), st));
+        EAE_TRY(run_layer(c, &p, 1, kLayerThin, umma_weights(c, 5, 1), -1, false, p.M, st));
     }
     { ProfScope prof(kProfCol2im, st); EAE_TRY(launch_col2im_k9s4(P, out_u8_dev, out_f32_dev, n, (int)h, (int)w, st)); }
     return 0;
@@ -572,6 +593,7 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
         }
     }
     if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
+    if (const char* env = getenv("EAE_NO_FUSE")) c->no_fuse = atoi(env);
     *out = c.release();
     return 0;
 }

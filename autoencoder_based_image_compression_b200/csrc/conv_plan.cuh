@@ -47,6 +47,8 @@ struct GemmPlan {
     int mode;
     int in_split;        // input stored parity-split: [n][(y&1)*2+(x&1)][Hin/2][Win/2][Cin]
     int out_split;       // output stored parity-split: [n][(y&1)*2+(x&1)][Hout/2][Wout/2][128]
+    int fuse;            // tensor path only: 0 none, 1 GDN, 2 IGDN applied to (acc + bias) before the store
+    const float* fuse_beta;
     int n_taps;
     uint32_t M;          // n * Hg * Wg
     Tap taps[kMaxTaps];

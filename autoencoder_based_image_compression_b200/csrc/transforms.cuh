@@ -19,7 +19,11 @@ struct UmmaWeights {
     const float* lo;
     int n_taps;
 };
-int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, bool exact3x, cudaStream_t st);
+// gamma: K-major hi/lo of the GDN weights when plan.fuse != 0 (kernel version 2), else NULL.
+int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
+                     cudaStream_t st);
+// 1: operands from shared memory, no fusion; 2 (default): A in TMEM, GDN / IGDN fusable (env EAE_UMMA_VERSION).
+int umma_version();
 // Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
 int umma_check_error(cudaStream_t st);
 // 0 if the tcgen05 path can run on the current device (sm_100), else an error code with message.
