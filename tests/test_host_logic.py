@@ -156,3 +156,21 @@ def test_stats_pack_and_summary():
     assert s['total_bits'] == 8128 and s['nb_dead_maps'] == 3 and s['nb_images'] == 2
     assert abs(s['rate_bpp'] - 8128/(512*768*2)) < 1e-15
     assert abs(s['psnr_db'] - 10*numpy.log10(255**2/(1000./(512*768*2)))) < 1e-12
+
+
+def test_drop_in_module_names_resolve(tmp_path):
+    """with the mirror directory on sys.path the reference's own import lines work."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, {root!r}); "
+            "sys.path.insert(0, {root!r} + '/autoencoder_based_image_compression_b200/kodak_tensorflow'); "
+            "import eae.batching, lossless.compression, lossless.interface_cython, tools.tools as tls; "
+            "from eae.graph.EntropyAutoencoder import EntropyAutoencoder; "
+            "from eae.graph.IsolatedDecoder import IsolatedDecoder; "
+            "import eae.graph.constants as csts; "
+            "assert csts.STRIDE_PROD == 16 and callable(eae.batching.encode_mini_batches) "
+            "and callable(lossless.compression.rescale_compress_lossless_maps) and callable(tls.quantize_per_map)"
+            ).format(root=root)
+    subprocess.check_call([sys.executable, '-c', code], cwd=str(tmp_path))
