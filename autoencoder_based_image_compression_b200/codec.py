@@ -64,7 +64,9 @@ class CodingParams(object):
 class Codec(object):
     """Both transforms of one EAE on one GPU."""
 
-    def __init__(self, weights, are_bin_widths_learned, device=0, math='fp32'):
+    def __init__(self, weights, are_bin_widths_learned, device=0, math='fp32', own_stream=False):
+        """``own_stream``: run this codec's work on its own non-blocking CUDA stream, so that several
+        codecs (pipeline slots) overlap on one GPU; by default the legacy default stream is used."""
         wts.validate(weights, are_bin_widths_learned)
         self.are_bin_widths_learned = bool(are_bin_widths_learned)
         self.device = device
@@ -83,11 +85,19 @@ class Codec(object):
         _native.check(_native.lib().eae_codec_create(ctypes.byref(self._handle), ctypes.byref(native_w),
                                                      int(self.are_bin_widths_learned), device))
         self.set_math(math)
+        self.stream = None
+        if own_stream:
+            stream = ctypes.c_void_p()
+            _native.check(_native.lib().eae_stream_create(ctypes.byref(stream)))
+            self.stream = stream
 
     def close(self):
         if getattr(self, '_handle', None):
             _native.lib().eae_codec_destroy(self._handle)
             self._handle = None
+        if getattr(self, 'stream', None):
+            _native.lib().eae_stream_destroy(self.stream)
+            self.stream = None
 
     def __del__(self):
         try:
@@ -111,7 +121,7 @@ class Codec(object):
         x = numpy.ascontiguousarray(luminances_uint8)
         (n, h, w) = x.shape[:3]
         y = numpy.empty((n, h//16, w//16, 128), dtype=numpy.float32)
-        _native.check(_native.lib().eae_encode_host(self.handle, _native.ptr(x), n, h, w, _native.ptr(y), None))
+        _native.check(_native.lib().eae_encode_host(self.handle, _native.ptr(x), n, h, w, _native.ptr(y), self.stream))
         return y
 
     def decode(self, quantized_y_float32, h_in=None, w_in=None):
@@ -120,7 +130,7 @@ class Codec(object):
         (n, hl, wl, _) = q.shape
         (h, w) = (hl*16, wl*16)
         out = numpy.empty((n, h, w, 1), dtype=numpy.uint8)
-        _native.check(_native.lib().eae_decode_host(self.handle, _native.ptr(q), n, h, w, _native.ptr(out), None))
+        _native.check(_native.lib().eae_decode_host(self.handle, _native.ptr(q), n, h, w, _native.ptr(out), self.stream))
         return out
 
     def decode_float(self, quantized_y_float32):
@@ -129,7 +139,7 @@ class Codec(object):
         (n, hl, wl, _) = q.shape
         out = numpy.empty((n, hl*16, wl*16, 1), dtype=numpy.float32)
         _native.check(_native.lib().eae_decode_float_host(self.handle, _native.ptr(q), n, hl*16, wl*16,
-                                                          _native.ptr(out), None))
+                                                          _native.ptr(out), self.stream))
         return out
 
     # ---- fused pipeline ----
@@ -152,12 +162,12 @@ class Codec(object):
         native_p = params.native()
         code = _native.lib().eae_compress_host(self.handle, ctypes.byref(native_p), _native.ptr(x), n, h, w,
                                                _native.ptr(container), container.size, ctypes.byref(nbytes),
-                                               ctypes.byref(stats), None)
+                                               ctypes.byref(stats), self.stream)
         if code == _native.ERR_ARGUMENT and container.size < bound and 'container needs' in _native.last_error():
             container = numpy.empty(int(bound), dtype=numpy.uint8)
             code = _native.lib().eae_compress_host(self.handle, ctypes.byref(native_p), _native.ptr(x), n, h, w,
                                                    _native.ptr(container), container.size, ctypes.byref(nbytes),
-                                                   ctypes.byref(stats), None)
+                                                   ctypes.byref(stats), self.stream)
         _native.check(code)
         out = container[:nbytes.value]
         if return_stats:
@@ -176,7 +186,7 @@ class Codec(object):
             out = numpy.empty((n, h, w), dtype=numpy.uint8)
         native_p = params.native()
         _native.check(_native.lib().eae_decompress_host(self.handle, ctypes.byref(native_p), _native.ptr(c), c.size,
-                                                        _native.ptr(out), out.size, None))
+                                                        _native.ptr(out), out.size, self.stream))
         return out
 
     def last_indices(self, n, h, w):

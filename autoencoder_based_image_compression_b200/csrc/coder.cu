@@ -8,6 +8,7 @@
 // The split point uses the reference's arithmetic literally: FP64 multiply (round-to-nearest, never
 // fused) followed by floor (BinaryArithmeticCoder.cpp:154).
 #include <memory>
+#include <stdlib.h>
 
 #include "coder_core.cuh"
 #include "common.cuh"
@@ -72,6 +73,12 @@ decode_streams_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t si
 // Threads per stream: one warp per stream until that would exceed ~32 warps per SM, then halve.
 inline uint32_t lanes_per_stream(uint32_t n_streams)
 {
+    static int forced = -1;   // env EAE_CODER_LANES (1, 2, 4, ... 32) overrides the heuristic
+    if (forced < 0) {
+        const char* env = getenv("EAE_CODER_LANES");
+        forced = env ? atoi(env) : 0;
+    }
+    if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return (uint32_t)forced;
     uint32_t lanes = 32;
     while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 32ull) lanes >>= 1;
     return lanes;
