@@ -339,6 +339,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 //
 //  TMEM columns: [0,128) accumulator, [128,256) norm accumulator, [256,512) 4 A slots x (32 hi + 32 lo).
 constexpr int kStages2 = 4;
+constexpr int kUmmaThreads2 = 320;               // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two conversion / epilogue sets
 constexpr int kStageBytes2 = 3 * kTileBytes;     // A (raw fp32 from TMA) | B_hi | B_lo
 constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
 constexpr uint32_t kTmemCols2 = 512;
@@ -387,7 +388,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
     return r;
 }
 
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(kUmmaThreads2, 1)
 gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
                   const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams2 p)
@@ -481,13 +482,17 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else {
-        // ===== warps 2..5: operand conversion into TMEM, then the epilogue =====
+        // ===== warps 2..9: operand conversion into TMEM, then the epilogue =====
+        // Two sets of four warps (a warp may only touch TMEM lanes 32 * (warp % 4) ..): set 0 converts the
+        // even iterations, set 1 the odd ones, so that two stages are in conversion at any time; in the
+        // final epilogue each set writes half of the 128 output channels.
         const int quarter = warp & 3;
+        const int set = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         bool ok = true;
         uint32_t r[32];
-        for (int it = 0; it < n_total && ok; it++) {
+        for (int it = set; it < n_total && ok; it += 2) {
             const int s = it % kStages2;
             ok = mbar_wait(&full[s], (it / kStages2) & 1, p.error_flag, 2);
             if (!ok) break;
@@ -506,7 +511,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     for (int i = 0; i < 32; i++) { const float x = __uint_as_float(r[i]); r[i] = __float_as_uint(x * x); }
                 }
             } else {
-                if (it == n_main) {
+                if (it == n_main || it == n_main + 1) {   // first GDN chunk of this set
                     ok = mbar_wait(acc_full, 0, p.error_flag, 3);
                     if (!ok) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -549,7 +554,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float* o = p.out + opix * kCout;
         const float* xi = p.xin + opix * kCout;
         #pragma unroll 1
-        for (int c0 = 0; c0 < kCout; c0 += 32) {
+        for (int c0 = set * 64; c0 < set * 64 + 64; c0 += 32) {
             uint32_t nr[32];
             tmem_ld32(lane_base + kColAcc + c0, r);
             if (p.fuse) tmem_ld32(lane_base + kColNrm + c0, nr);
@@ -757,7 +762,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
             attr2_done = true;
         }
-        gemm_umma2_kernel<<<grid, kUmmaThreads, kSmemBytes2, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+        gemm_umma2_kernel<<<grid, kUmmaThreads2, kSmemBytes2, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
         EAE_LAUNCH_OK();
         return 0;
     }
