@@ -357,9 +357,41 @@ struct UmmaParams2 {
     int mode;                // EpilogueMode of a standalone launch
     int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
     int exact_main;          // 3xTF32 for the main contraction
+    int cluster;             // CTAs per cluster (1, 2 or 4): each loads 1/cluster of every B tile and multicasts it
+    int n_tiles;             // real tiles; the grid is rounded up to a multiple of `cluster`
     uint32_t* error_flag;
     UmmaTap taps[kMaxTaps];
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// B slice load that lands at the same shared-memory offset (and signals the same mbarrier offset) in every
+// CTA of `mask`.
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1),
+          "r"(c2)
+        : "memory");
+}
+// MMA completion -> the same mbarrier in every CTA of `mask` (stage released cluster-wide).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate)
 {
@@ -405,15 +437,22 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
+    // Phantom CTAs that pad the grid to a whole cluster redo the last tile without storing it: they must
+    // still load and multicast their share of every B tile.
+    const bool store_ok = (int)blockIdx.x < p.n_tiles;
+    const int tile = store_ok ? (int)blockIdx.x : p.n_tiles - 1;
+    const int img = tile / tiles_per_img;
+    const int trem = tile - img * tiles_per_img;
+    const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+    const int b_rows = kCout / p.cluster;      // rows of every B tile this CTA loads
     const int a0 = (trem / p.tiles_x) * p.tile_h, b0 = (trem % p.tiles_x) * p.tile_w;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kStages2; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&split[s], 128);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], (uint32_t)p.cluster);   // one MMA commit per CTA of the cluster
         }
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
@@ -426,6 +465,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();     // every CTA's barriers exist before any remote arrive / multicast
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -444,13 +484,29 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const UmmaTap tap = p.taps[t];
                     mbar_expect_tx(&full[s], p.exact_main ? 3 * kTileBytes : 2 * kTileBytes);
                     tma_load_5d(st, &map_a, &full[s], kc * kChunkK, b0 + tap.fx, a0 + tap.fy, tap.plane, img);
-                    tma_load_3d(st + kTileBytes, &map_b_hi, &full[s], kc * kChunkK, 0, tap.w_tap);
-                    if (p.exact_main) tma_load_3d(st + 2 * kTileBytes, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
+                    const int boff = (int)crank * b_rows * 128;
+                    if (p.cluster > 1) {
+                        tma_load_3d_mc(st + kTileBytes + boff, &map_b_hi, &full[s], kc * kChunkK, (int)crank * b_rows,
+                                       tap.w_tap, cmask);
+                        if (p.exact_main)
+                            tma_load_3d_mc(st + 2 * kTileBytes + boff, &map_b_lo, &full[s], kc * kChunkK,
+                                           (int)crank * b_rows, tap.w_tap, cmask);
+                    } else {
+                        tma_load_3d(st + kTileBytes, &map_b_hi, &full[s], kc * kChunkK, 0, tap.w_tap);
+                        if (p.exact_main) tma_load_3d(st + 2 * kTileBytes, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
+                    }
                 } else {
                     const int kc = it - n_main;     // gamma chunk
                     mbar_expect_tx(&full[s], 2 * kTileBytes);
-                    tma_load_3d(st + kTileBytes, &map_g_hi, &full[s], kc * kChunkK, 0, 0);
-                    tma_load_3d(st + 2 * kTileBytes, &map_g_lo, &full[s], kc * kChunkK, 0, 0);
+                    const int boff = (int)crank * b_rows * 128;
+                    if (p.cluster > 1) {
+                        tma_load_3d_mc(st + kTileBytes + boff, &map_g_hi, &full[s], kc * kChunkK, (int)crank * b_rows, 0, cmask);
+                        tma_load_3d_mc(st + 2 * kTileBytes + boff, &map_g_lo, &full[s], kc * kChunkK, (int)crank * b_rows, 0,
+                                       cmask);
+                    } else {
+                        tma_load_3d(st + kTileBytes, &map_g_hi, &full[s], kc * kChunkK, 0, 0);
+                        tma_load_3d(st + 2 * kTileBytes, &map_g_lo, &full[s], kc * kChunkK, 0, 0);
+                    }
                 }
             }
         }
@@ -476,7 +532,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         umma_tf32_ts(d, a_slot + 8 * k, make_desc(st + 2 * kTileBytes + k * 32), 1u);
                     }
                 }
-                umma_commit(&empty[s]);
+                if (p.cluster > 1) umma_commit_mc(&empty[s], cmask); else umma_commit(&empty[s]);
                 if (it == n_main - 1) umma_commit(acc_full);
                 if (gdn && it == n_total - 1) umma_commit(nrm_full);
             }
@@ -542,7 +598,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (ok) ok = mbar_wait(p.fuse ? nrm_full : acc_full, 0, p.error_flag, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int a = a0 + row / p.tile_w, b = b0 + row % p.tile_w;
-        const bool valid = ok && a < p.Hg && b < p.Wg;
+        const bool valid = ok && store_ok && a < p.Hg && b < p.Wg;
         size_t opix = 0;
         if (valid) {
             const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
@@ -596,6 +652,8 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
     }
+    // No CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers.
+    if (p.cluster > 1) cluster_sync_all();
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -734,8 +792,21 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
     const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
     if (umma_version() == 2) {
+        // Cluster size: B tiles are identical for every CTA, so the CTAs of a cluster split each B tile and
+        // multicast their slices (env EAE_UMMA_CLUSTER: 1, 2 or 4; default 2 when there are enough tiles).
+        static int cs_env = -1;
+        if (cs_env < 0) { const char* env = getenv("EAE_UMMA_CLUSTER"); cs_env = env ? atoi(env) : 0; }
+        unsigned cs = (cs_env == 1 || cs_env == 2 || cs_env == 4) ? (unsigned)cs_env : 2u;
+        if (grid < 2 * cs) cs = 1;
+        if (cs > 1) {
+            const uint32_t sbox[3] = {kChunkK, kCout / cs, 1};
+            EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, sbox));
+            EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, sbox));
+        }
         UmmaParams2 q;
         memset(&q, 0, sizeof q);
+        q.cluster = (int)cs;
+        q.n_tiles = (int)grid;
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;
         q.tile_w = p.tile_w; q.tile_h = p.tile_h; q.tiles_x = p.tiles_x; q.tiles_y = p.tiles_y;
         q.Hg = p.Hg; q.Wg = p.Wg;
@@ -754,15 +825,27 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 return EAE_ERR_ARGUMENT;
             }
             const uint64_t gdims[3] = {kCout, kCout, 1};
-            EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
-            EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
+            const uint32_t gbox[3] = {kChunkK, kCout / cs, 1};
+            EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, gbox));
+            EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, gbox));
         }
         static bool attr2_done = false;
         if (!attr2_done) {
             EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
             attr2_done = true;
         }
-        gemm_umma2_kernel<<<grid, kUmmaThreads2, kSmemBytes2, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(((grid + cs - 1) / cs) * cs);
+        cfg.blockDim = dim3(kUmmaThreads2);
+        cfg.dynamicSmemBytes = kSmemBytes2;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        EAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_umma2_kernel, map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q));
         EAE_LAUNCH_OK();
         return 0;
     }
