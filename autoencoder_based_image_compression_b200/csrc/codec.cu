@@ -167,7 +167,7 @@ int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw
 // Can the GDN / IGDN that follows a contraction of this kind run inside its epilogue?
 bool can_fuse(const eae_codec* c, int kind)
 {
-    return c->math != EAE_MATH_FP32_SIMT && umma_version() == 2 && ((c->umma_mask >> kind) & 1) &&
+    return c->math != EAE_MATH_FP32_SIMT && umma_version() >= 2 && ((c->umma_mask >> kind) & 1) &&
            ((c->umma_mask >> kLayerGdn) & 1) && !c->no_fuse;
 }
 

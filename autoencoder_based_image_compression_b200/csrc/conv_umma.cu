@@ -359,6 +359,8 @@ struct UmmaParams2 {
     int exact_main;          // 3xTF32 for the main contraction
     int cluster;             // CTAs per cluster (1, 2 or 4): each loads 1/cluster of every B tile and multicasts it
     int n_tiles;             // real tiles; the grid is rounded up to a multiple of `cluster`
+    int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
+    int debug;               // timing experiments (env EAE_UMMA_DEBUG): 1 no conversion, 2 no MMA, 4 no B loads, 8 no A loads
     uint32_t* error_flag;
     UmmaTap taps[kMaxTaps];
 };
@@ -482,10 +484,13 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (it < n_main) {
                     const int t = it / p.kchunks, kc = it - t * p.kchunks;
                     const UmmaTap tap = p.taps[t];
-                    mbar_expect_tx(&full[s], p.exact_main ? 3 * kTileBytes : 2 * kTileBytes);
-                    tma_load_5d(st, &map_a, &full[s], kc * kChunkK, b0 + tap.fx, a0 + tap.fy, tap.plane, img);
+                    const bool ld_a = !(p.debug & 8), ld_b = !(p.debug & 4);      // timing experiments only
+                    const uint32_t bytes = (ld_a ? kTileBytes : 0) + (ld_b ? (p.exact_main ? 2 : 1) * kTileBytes : 0);
+                    if (bytes) mbar_expect_tx(&full[s], bytes); else mbar_arrive(&full[s]);
+                    if (ld_a) tma_load_5d(st, &map_a, &full[s], kc * kChunkK, b0 + tap.fx, a0 + tap.fy, tap.plane, img);
                     const int boff = (int)crank * b_rows * 128;
-                    if (p.cluster > 1) {
+                    if (!ld_b) {
+                    } else if (p.cluster > 1) {
                         tma_load_3d_mc(st + kTileBytes + boff, &map_b_hi, &full[s], kc * kChunkK, (int)crank * b_rows,
                                        tap.w_tap, cmask);
                         if (p.exact_main)
@@ -525,6 +530,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t a_slot = tmem_base + kColA + 64u * (uint32_t)s;
                 #pragma unroll
                 for (int k = 0; k < kChunkK / 8; k++) {
+                    if (p.debug & 2) break;
                     const uint64_t b_hi = make_desc(st + kTileBytes + k * 32);
                     umma_tf32_ts(d, a_slot + 8 * k, b_hi, (first && k == 0) ? 0u : 1u);
                     if (exact) {
@@ -553,6 +559,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ok = mbar_wait(&full[s], (it / kStages2) & 1, p.error_flag, 2);
             if (!ok) break;
             const bool gdn = it >= n_main;
+            if (p.debug & 1) { mbar_arrive(&split[s]); continue; }
             if (!gdn) {
                 // this thread's row of the SWIZZLE_128B tile: 16-byte chunk c sits at chunk (c ^ (row & 7))
                 const uint8_t* rowp = smem + s * kStageBytes2 + row * 128;
@@ -656,6 +663,289 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (p.cluster > 1) cluster_sync_all();
 }
 
+// =================================================================================================
+// Version 3: 256 output positions per CTA (two 128-row halves, two TMEM accumulators).
+//
+// Measured on version 2 (profiles/): with the loads, the conversion and the MMAs all knocked out, the k5
+// convolutions still took half of their time, i.e. the kernel was bound by per-tile fixed cost (TMEM
+// allocation, barrier setup, an uncoalesced epilogue) and by the latency of the four-hop mbarrier ring
+// with only four 48 KB stages in flight, not by the tensor pipe or by L2. Version 3 therefore
+//  * doubles the work per ring iteration and per CTA: one B (weight) stage feeds two accumulators, so the
+//    same shared memory holds twice the MMA work per stage and every weight tile is fetched half as often;
+//  * stages the epilogue through shared memory and writes whole 512-byte pixel rows per warp instruction;
+//  * keeps the norm accumulators of both halves in TMEM during the fused GDN / IGDN: the (x^2)_hi / (x^2)_lo
+//    operands of that second contraction are written to shared memory in the canonical swizzled layout.
+//
+//  TMEM: [0,128) ACC0, [128,256) ACC1, [256,512) two A slots of 128 columns (hi0 lo0 hi1 lo1) during the main
+//        loop, then NRM0 [256,384) and NRM1 [384,512).
+//  smem: 3 stages x { A0 16K | A1 16K | B_hi 16K | B_lo 16K }.
+constexpr int kStages3 = 3;
+constexpr int kStageBytes3 = 4 * kTileBytes;
+constexpr int kSmemBytes3 = kStages3 * kStageBytes3 + 1024 + 256;
+constexpr int kUmmaThreads3 = 320;
+constexpr uint32_t kCol3Acc0 = 0, kCol3Acc1 = 128, kCol3Slots = 256, kCol3Nrm0 = 256, kCol3Nrm1 = 384;
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+__global__ void __launch_bounds__(kUmmaThreads3, 1)
+gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+                  const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams2 p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages3 * kStageBytes3);
+    uint64_t* full = bars;
+    uint64_t* split = bars + kStages3;
+    uint64_t* empty = bars + 2 * kStages3;
+    uint64_t* acc_full = bars + 3 * kStages3;
+    uint64_t* nrm_full = bars + 3 * kStages3 + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages3 + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile = tile_w x (2 * tile_h) positions: half h covers rows [a0 + h * tile_h, +tile_h)
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int a0 = (trem / p.tiles_x) * (p.tile_h + p.half_da), b0 = (trem % p.tiles_x) * (p.tile_w + p.half_db);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages3; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 128);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(nrm_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_main = p.n_taps * p.kchunks;
+    const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
+    const int n_total = n_main + n_gdn;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < n_total; it++) {
+                const int s = it % kStages3;
+                if (!mbar_wait(&empty[s], ((it / kStages3) & 1) ^ 1, p.error_flag, 0)) break;
+                uint8_t* st = smem + s * kStageBytes3;
+                if (it < n_main) {
+                    const int t = it / p.kchunks, kc = it - t * p.kchunks;
+                    const UmmaTap tap = p.taps[t];
+                    mbar_expect_tx(&full[s], (p.exact_main ? 4 : 3) * kTileBytes);
+                    tma_load_5d(st, &map_a, &full[s], kc * kChunkK, b0 + tap.fx, a0 + tap.fy, tap.plane, img);
+                    tma_load_5d(st + kTileBytes, &map_a, &full[s], kc * kChunkK, b0 + p.half_db + tap.fx,
+                                a0 + p.half_da + tap.fy, tap.plane, img);
+                    tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full[s], kc * kChunkK, 0, tap.w_tap);
+                    if (p.exact_main) tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
+                } else {
+                    const int kc = (it - n_main) & 3;     // gamma chunk (each half re-loads it)
+                    mbar_expect_tx(&full[s], 2 * kTileBytes);
+                    tma_load_3d(st + 2 * kTileBytes, &map_g_hi, &full[s], kc * kChunkK, 0, 0);
+                    tma_load_3d(st + 3 * kTileBytes, &map_g_lo, &full[s], kc * kChunkK, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int it = 0; it < n_total; it++) {
+                const int s = it % kStages3;
+                if (!mbar_wait(&split[s], (it / kStages3) & 1, p.error_flag, 1)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * kStageBytes3);
+                if (it < n_main) {
+                    const uint32_t slot = tmem_base + kCol3Slots + 128u * (uint32_t)(it & 1);
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t d = tmem_base + (h ? kCol3Acc1 : kCol3Acc0);
+                        const uint32_t a_hi = slot + 64u * (uint32_t)h, a_lo = a_hi + 32u;
+                        #pragma unroll
+                        for (int k = 0; k < kChunkK / 8; k++) {
+                            const uint64_t b_hi = make_desc(st + 2 * kTileBytes + k * 32);
+                            umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
+                            if (p.exact_main) {
+                                umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
+                                umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + 3 * kTileBytes + k * 32), 1u);
+                            }
+                        }
+                    }
+                } else {
+                    // fused GDN: NRM_h += (x^2)_hi g_hi + (x^2)_lo g_hi + (x^2)_hi g_lo, operands in shared memory
+                    const int g = it - n_main, h = g >> 2, kc = g & 3;
+                    const uint32_t d = tmem_base + (h ? kCol3Nrm1 : kCol3Nrm0);
+                    #pragma unroll
+                    for (int k = 0; k < kChunkK / 8; k++) {
+                        const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
+                        const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
+                        umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
+                        umma_tf32(d, x_lo, g_hi, 1u);
+                        umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (it == n_main - 1) umma_commit(acc_full);
+                if (n_gdn && it == n_total - 1) umma_commit(nrm_full);
+            }
+        }
+    } else {
+        // ===== warps 2..9: two conversion / epilogue sets (set = iteration parity) =====
+        const int quarter = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        bool ok = true;
+        uint32_t r[32], hi[32];
+        for (int it = set; it < n_total && ok; it += 2) {
+            const int s = it % kStages3;
+            ok = mbar_wait(&full[s], (it / kStages3) & 1, p.error_flag, 2);
+            if (!ok) break;
+            uint8_t* st = smem + s * kStageBytes3;
+            if (it < n_main) {
+                // TMEM slot (it & 1) was last read by the MMAs of iteration it - 2
+                if (it >= 2) {
+                    ok = mbar_wait(&empty[(it - 2) % kStages3], ((it - 2) / kStages3) & 1, p.error_flag, 5);
+                    if (!ok) break;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t slot = lane_base + kCol3Slots + 128u * (uint32_t)(it & 1);
+                #pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint8_t* rowp = st + h * kTileBytes + row * 128;
+                    #pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (row & 7)) << 4));
+                        r[4 * c + 0] = __float_as_uint(v.x); r[4 * c + 1] = __float_as_uint(v.y);
+                        r[4 * c + 2] = __float_as_uint(v.z); r[4 * c + 3] = __float_as_uint(v.w);
+                    }
+                    if (p.mode != kEpiBias) {
+                        #pragma unroll
+                        for (int i = 0; i < 32; i++) { const float x = __uint_as_float(r[i]); r[i] = __float_as_uint(x * x); }
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 32; i++) hi[i] = to_tf32(__uint_as_float(r[i]));
+                    tmem_st32(slot + 64u * (uint32_t)h, hi);
+                    if (p.exact_main) {
+                        #pragma unroll
+                        for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(hi[i]));
+                        tmem_st32(slot + 64u * (uint32_t)h + 32u, r);
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            } else {
+                if (it == n_main || it == n_main + 1) {
+                    ok = mbar_wait(acc_full, 0, p.error_flag, 3);
+                    if (!ok) break;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const int g = it - n_main, h = g >> 2, c0 = (g & 3) * kChunkK;
+                tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                uint8_t* rowp = st + row * 128;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float4 xh, xl;
+                    float x;
+                    x = __uint_as_float(r[4 * c + 0]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 0); x *= x;
+                    xh.x = __uint_as_float(to_tf32(x)); xl.x = x - xh.x;
+                    x = __uint_as_float(r[4 * c + 1]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 1); x *= x;
+                    xh.y = __uint_as_float(to_tf32(x)); xl.y = x - xh.y;
+                    x = __uint_as_float(r[4 * c + 2]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 2); x *= x;
+                    xh.z = __uint_as_float(to_tf32(x)); xl.z = x - xh.z;
+                    x = __uint_as_float(r[4 * c + 3]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 3); x *= x;
+                    xh.w = __uint_as_float(to_tf32(x)); xl.w = x - xh.w;
+                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = xh;
+                    *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            mbar_arrive(&split[s]);
+        }
+        if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (stage h of the ring,
+        // four swizzled [128 x 32] sub-tiles) -> coalesced 512-byte rows.
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            uint8_t* stage = smem + h * kStageBytes3;
+            #pragma unroll 1
+            for (int cc = 0; cc < 2; cc++) {
+                const int c0 = set * 64 + cc * 32;
+                tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                if (n_gdn) tmem_ld32(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
+                uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float x = __uint_as_float(r[4 * c + j]);
+                        if (p.bias) x += __ldg(p.bias + c0 + 4 * c + j);
+                        if (n_gdn) {
+                            const float nn = __fsqrt_rn(__uint_as_float(hi[4 * c + j]) + __ldg(p.beta + c0 + 4 * c + j));
+                            x = p.fuse == 1 ? __fdiv_rn(x, nn) : __fmul_rn(x, nn);
+                        }
+                        v[j] = x;
+                    }
+                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+        named_bar_sync(1, 256);     // both sets finished staging
+        const int wq = warp - 2;    // 0..7: rows wq, wq + 8, ... of each half
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const uint8_t* stage = smem + h * kStageBytes3;
+            #pragma unroll 1
+            for (int rr = wq; rr < kTileM; rr += 8) {
+                const int a = a0 + h * p.half_da + rr / p.tile_w, b = b0 + h * p.half_db + rr % p.tile_w;
+                if (!(ok && a < p.Hg && b < p.Wg)) continue;
+                const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
+                size_t opix;
+                if (p.out_split)
+                    opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
+                else
+                    opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+                float4 v = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 +
+                                                            (((lane & 7) ^ (rr & 7)) << 4));
+                if (!n_gdn && p.mode != kEpiBias) {
+                    // standalone GDN / IGDN: v holds norm (+ beta via bias); combine with the un-squared input
+                    const float4 x = *reinterpret_cast<const float4*>(p.xin + opix * kCout + lane * 4);
+                    if (p.mode == kEpiGdn) {
+                        v.x = __fdiv_rn(x.x, __fsqrt_rn(v.x)); v.y = __fdiv_rn(x.y, __fsqrt_rn(v.y));
+                        v.z = __fdiv_rn(x.z, __fsqrt_rn(v.z)); v.w = __fdiv_rn(x.w, __fsqrt_rn(v.w));
+                    } else {
+                        v.x = __fmul_rn(x.x, __fsqrt_rn(v.x)); v.y = __fmul_rn(x.y, __fsqrt_rn(v.y));
+                        v.z = __fmul_rn(x.z, __fsqrt_rn(v.z)); v.w = __fmul_rn(x.w, __fsqrt_rn(v.w));
+                    }
+                }
+                *reinterpret_cast<float4*>(p.out + opix * kCout + lane * 4) = v;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -732,7 +1022,8 @@ int umma_version()
     static int v = 0;
     if (!v) {
         const char* env = getenv("EAE_UMMA_VERSION");
-        v = (env && atoi(env) == 1) ? 1 : 2;
+        v = env ? atoi(env) : 3;
+        if (v < 1 || v > 3) v = 3;
     }
     return v;
 }
@@ -791,6 +1082,45 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
     const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
+    if (umma_version() == 3) {
+        UmmaParams2 q;
+        memset(&q, 0, sizeof q);
+        q.n_taps = p.n_taps; q.kchunks = p.kchunks;
+        q.tile_w = p.tile_w; q.tile_h = p.tile_h;
+        if (plan.Hg == 1) { q.half_da = 0; q.half_db = p.tile_w; } else { q.half_da = p.tile_h; q.half_db = 0; }
+        q.tiles_x = (plan.Wg + q.tile_w + q.half_db - 1) / (q.tile_w + q.half_db);
+        q.tiles_y = (plan.Hg + q.tile_h + q.half_da - 1) / (q.tile_h + q.half_da);
+        q.Hg = p.Hg; q.Wg = p.Wg;
+        q.out = p.out; q.bias = p.bias; q.beta = plan.fuse_beta; q.xin = p.xin;
+        q.Hout = p.Hout; q.Wout = p.Wout; q.out_mul = p.out_mul; q.out_r = p.out_r; q.out_s = p.out_s;
+        q.out_split = p.out_split;
+        q.mode = p.mode;
+        q.fuse = plan.fuse;
+        q.exact_main = exact3x ? 1 : 0;
+        q.cluster = 1;
+        q.error_flag = p.error_flag;
+        memcpy(q.taps, p.taps, sizeof q.taps);
+        const uint32_t grid3 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
+        q.n_tiles = (int)grid3;
+        CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo;
+        if (plan.fuse) {
+            if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias) {
+                set_error("gemm_umma: fused GDN needs gamma hi/lo, beta and a bias-mode contraction");
+                return EAE_ERR_ARGUMENT;
+            }
+            const uint64_t gdims[3] = {kCout, kCout, 1};
+            EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
+            EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
+        }
+        static bool attr3_done = false;
+        if (!attr3_done) {
+            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
+            attr3_done = true;
+        }
+        gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+        EAE_LAUNCH_OK();
+        return 0;
+    }
     if (umma_version() == 2) {
         // Cluster size: B tiles are identical for every CTA, so the CTAs of a cluster split each B tile and
         // multicast their slices (env EAE_UMMA_CLUSTER: 1, 2 or 4; default 2 when there are enough tiles).
@@ -807,6 +1137,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         memset(&q, 0, sizeof q);
         q.cluster = (int)cs;
         q.n_tiles = (int)grid;
+        { static int dbg = -1; if (dbg < 0) { const char* e = getenv("EAE_UMMA_DEBUG"); dbg = e ? atoi(e) : 0; } q.debug = dbg; }
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;
         q.tile_w = p.tile_w; q.tile_h = p.tile_h; q.tiles_x = p.tiles_x; q.tiles_y = p.tiles_y;
         q.Hg = p.Hg; q.Wg = p.Wg;
@@ -849,7 +1180,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         EAE_LAUNCH_OK();
         return 0;
     }
-    if (plan.fuse) { set_error("gemm_umma: fused GDN needs kernel version 2"); return EAE_ERR_ARGUMENT; }
+    if (plan.fuse) { set_error("gemm_umma: fused GDN needs kernel version 2 or 3"); return EAE_ERR_ARGUMENT; }
     if (exact3x) {
         static bool attr_done = false;
         if (!attr_done) {

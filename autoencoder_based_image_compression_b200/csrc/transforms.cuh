@@ -22,7 +22,8 @@ struct UmmaWeights {
 // gamma: K-major hi/lo of the GDN weights when plan.fuse != 0 (kernel version 2), else NULL.
 int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
                      cudaStream_t st);
-// 1: operands from shared memory, no fusion; 2 (default): A in TMEM, GDN / IGDN fusable (env EAE_UMMA_VERSION).
+// 1: operands from shared memory, no fusion; 2: A in TMEM, GDN / IGDN fusable; 3 (default): 2 + 256 rows per CTA
+// and a coalesced epilogue (env EAE_UMMA_VERSION).
 int umma_version();
 // Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
 int umma_check_error(cudaStream_t st);
