@@ -589,13 +589,14 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             const bool exact = gdn || p.exact_main;
-            uint32_t hi[32];
-            #pragma unroll
-            for (int i = 0; i < 32; i++) hi[i] = to_tf32(__uint_as_float(r[i]));
-            tmem_st32(lane_base + kColA + 64u * (uint32_t)s, hi);
+            // hi = the fp32 value itself (the tensor core reads only the TF32 bits, i.e. truncates);
+            // lo = x - trunc_tf32(x), exact in fp32. One LOP + one FADD per element: cvt.rna here made the
+            // conversion, not the MMA, the slowest stage of the ring (scripts/ubench.cu, profiles/).
+            tmem_st32(lane_base + kColA + 64u * (uint32_t)s, r);
             if (exact) {
                 #pragma unroll
-                for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(hi[i]));
+                for (int i = 0; i < 32; i++)
+                    r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
                 tmem_st32(lane_base + kColA + 64u * (uint32_t)s + 32u, r);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -836,12 +837,12 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         #pragma unroll
                         for (int i = 0; i < 32; i++) { const float x = __uint_as_float(r[i]); r[i] = __float_as_uint(x * x); }
                     }
-                    #pragma unroll
-                    for (int i = 0; i < 32; i++) hi[i] = to_tf32(__uint_as_float(r[i]));
-                    tmem_st32(slot + 64u * (uint32_t)h, hi);
+                    // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x)
+                    tmem_st32(slot + 64u * (uint32_t)h, r);
                     if (p.exact_main) {
                         #pragma unroll
-                        for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(hi[i]));
+                        for (int i = 0; i < 32; i++)
+                            r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
                         tmem_st32(slot + 64u * (uint32_t)h + 32u, r);
                     }
                 }
@@ -861,13 +862,13 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     float4 xh, xl;
                     float x;
                     x = __uint_as_float(r[4 * c + 0]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 0); x *= x;
-                    xh.x = __uint_as_float(to_tf32(x)); xl.x = x - xh.x;
+                    xh.x = x; xl.x = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     x = __uint_as_float(r[4 * c + 1]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 1); x *= x;
-                    xh.y = __uint_as_float(to_tf32(x)); xl.y = x - xh.y;
+                    xh.y = x; xl.y = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     x = __uint_as_float(r[4 * c + 2]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 2); x *= x;
-                    xh.z = __uint_as_float(to_tf32(x)); xl.z = x - xh.z;
+                    xh.z = x; xl.z = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     x = __uint_as_float(r[4 * c + 3]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 3); x *= x;
-                    xh.w = __uint_as_float(to_tf32(x)); xl.w = x - xh.w;
+                    xh.w = x; xl.w = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = xh;
                     *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
                 }
