@@ -359,6 +359,7 @@ struct UmmaParams2 {
     int exact_main;          // 3xTF32 for the main contraction
     int cluster;             // CTAs per cluster (1, 2 or 4): each loads 1/cluster of every B tile and multicasts it
     int n_tiles;             // real tiles; the grid is rounded up to a multiple of `cluster`
+    int tile_w_log2;
     int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
     int debug;               // timing experiments (env EAE_UMMA_DEBUG): 1 no conversion, 2 no MMA, 4 no B loads, 8 no A loads
     uint32_t* error_flag;
@@ -859,17 +860,19 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 uint8_t* rowp = st + row * 128;
                 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    float4 xh, xl;
-                    float x;
-                    x = __uint_as_float(r[4 * c + 0]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 0); x *= x;
-                    xh.x = x; xl.x = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    x = __uint_as_float(r[4 * c + 1]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 1); x *= x;
-                    xh.y = x; xl.y = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    x = __uint_as_float(r[4 * c + 2]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 2); x *= x;
-                    xh.z = x; xl.z = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    x = __uint_as_float(r[4 * c + 3]); if (p.bias) x += __ldg(p.bias + c0 + 4 * c + 3); x *= x;
-                    xh.w = x; xl.w = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = xh;
+                    float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                    if (p.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
+                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                    }
+                    x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
+                    float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
+                    xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
                     *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -893,18 +896,25 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
                 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    float v[4];
-                    #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float x = __uint_as_float(r[4 * c + j]);
-                        if (p.bias) x += __ldg(p.bias + c0 + 4 * c + j);
-                        if (n_gdn) {
-                            const float nn = __fsqrt_rn(__uint_as_float(hi[4 * c + j]) + __ldg(p.beta + c0 + 4 * c + j));
-                            x = p.fuse == 1 ? __fdiv_rn(x, nn) : __fmul_rn(x, nn);
-                        }
-                        v[j] = x;
+                    float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                    if (p.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                     }
-                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (n_gdn) {
+                        // x * rsqrt(norm + beta) (GDN) or x * (n * rsqrt(n)) (IGDN): the 2-ulp MUFU forms; their error
+                        // (2^-22) is below that of the 3xTF32 contraction that produced x.
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * c));
+                        const float n0 = __uint_as_float(hi[4 * c]) + be.x, n1 = __uint_as_float(hi[4 * c + 1]) + be.y;
+                        const float n2 = __uint_as_float(hi[4 * c + 2]) + be.z, n3 = __uint_as_float(hi[4 * c + 3]) + be.w;
+                        if (p.fuse == 1) {
+                            v.x *= rsqrtf(n0); v.y *= rsqrtf(n1); v.z *= rsqrtf(n2); v.w *= rsqrtf(n3);
+                        } else {
+                            v.x *= n0 * rsqrtf(n0); v.y *= n1 * rsqrtf(n1); v.z *= n2 * rsqrtf(n2); v.w *= n3 * rsqrtf(n3);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = v;
                 }
             }
         }
@@ -915,7 +925,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint8_t* stage = smem + h * kStageBytes3;
             #pragma unroll 1
             for (int rr = wq; rr < kTileM; rr += 8) {
-                const int a = a0 + h * p.half_da + rr / p.tile_w, b = b0 + h * p.half_db + rr % p.tile_w;
+                const int a = a0 + h * p.half_da + (rr >> p.tile_w_log2), b = b0 + h * p.half_db + (rr & (p.tile_w - 1));
                 if (!(ok && a < p.Hg && b < p.Wg)) continue;
                 const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
                 size_t opix;
@@ -1088,6 +1098,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         memset(&q, 0, sizeof q);
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;
         q.tile_w = p.tile_w; q.tile_h = p.tile_h;
+        q.tile_w_log2 = p.tile_w == 128 ? 7 : 4;
         if (plan.Hg == 1) { q.half_da = 0; q.half_db = p.tile_w; } else { q.half_da = p.tile_h; q.half_db = 0; }
         q.tiles_x = (plan.Wg + q.tile_w + q.half_db - 1) / (q.tile_w + q.half_db);
         q.tiles_y = (plan.Hg + q.tile_h + q.half_da - 1) / (q.tile_h + q.half_da);
