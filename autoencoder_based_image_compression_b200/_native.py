@@ -105,6 +105,7 @@ PROTOTYPES = {
     'eae_codec_destroy': (c_int, [c_void_p]),
     'eae_codec_set_math': (c_int, [c_void_p, c_int]),
     'eae_codec_get_math': (c_int, [c_void_p]),
+    'eae_codec_set_coder_lanes': (c_int, [c_void_p, u32]),
     'eae_encode_host': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
     'eae_encode_dev': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),
     'eae_decode_host': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p, c_void_p]),

@@ -115,6 +115,10 @@ class Codec(object):
         mode = _native.MATH_NAMES[math] if isinstance(math, str) else int(math)
         _native.check(_native.lib().eae_codec_set_math(self.handle, mode))
 
+    def set_coder_lanes(self, lanes):
+        """GPU threads per coded stream (0 = auto / lowest latency; 1, 2, 4 = throughput-oriented packing)."""
+        _native.check(_native.lib().eae_codec_set_coder_lanes(self.handle, int(lanes)))
+
     # ---- transforms, host arrays (the reference's sess.run boundaries) ----
     def encode(self, luminances_uint8):
         """uint8 [n, h, w, 1] (or [n, h, w]) -> float32 [n, h/16, w/16, 128] (components.py:86-142)."""

@@ -18,6 +18,7 @@ struct eae_codec {
     int learned = 0;   // are_bin_widths_learned: 4 GDN/IGDN instead of 6
     int math = EAE_MATH_FP32_SIMT;
     int umma_mask = 0xF;   // which layer kinds run on tensor cores (debug: env EAE_UMMA_LAYERS)
+    uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
     cudaStream_t own_stream = nullptr;
 
@@ -426,7 +427,8 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
         ProfScope prof(kProfCoderEncode, st);
         EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
-                                      c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st));
+                                      c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st,
+                                      c->coder_lanes));
     }
     ProfScope prof_pack(kProfPack, st);
     stream_offsets_kernel<<<1, 1024, 0, st>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
@@ -477,7 +479,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
         EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
                                       container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
-                                      c->err.as<uint32_t>(), st));
+                                      c->err.as<uint32_t>(), st, c->coder_lanes));
     }
     c->last_idx_elems = (uint64_t)n_streams * hw3;
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
@@ -614,6 +616,14 @@ extern "C" int eae_codec_set_math(eae_codec_t* c, int mode)
     }
     if (mode != EAE_MATH_FP32_SIMT) EAE_TRY(umma_available());
     c->math = mode;
+    return 0;
+}
+
+extern "C" int eae_codec_set_coder_lanes(eae_codec_t* c, uint32_t lanes)
+{
+    if (!c) { set_error("NULL codec"); return EAE_ERR_NULL; }
+    if (lanes > 32 || (lanes & (lanes - 1)) != 0) { set_error("coder lanes must be 0 or a power of two <= 32"); return EAE_ERR_ARGUMENT; }
+    c->coder_lanes = lanes;
     return 0;
 }
 

@@ -71,7 +71,7 @@ decode_streams_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t si
 }
 
 // Threads per stream: one warp per stream until that would exceed ~32 warps per SM, then halve.
-inline uint32_t lanes_per_stream(uint32_t n_streams)
+inline uint32_t lanes_per_stream(uint32_t n_streams, uint32_t requested)
 {
     static int forced = -1;   // env EAE_CODER_LANES (1, 2, 4, ... 32) overrides the heuristic
     if (forced < 0) {
@@ -79,6 +79,7 @@ inline uint32_t lanes_per_stream(uint32_t n_streams)
         forced = env ? atoi(env) : 0;
     }
     if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return (uint32_t)forced;
+    if (requested >= 1 && requested <= 32 && (requested & (requested - 1)) == 0) return requested;
     uint32_t lanes = 32;
     while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 32ull) lanes >>= 1;
     return lanes;
@@ -176,10 +177,10 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, uint8_t* bac_slots, uint8_t* byp_slots,
                           uint32_t slot_bytes, uint32_t* bac_bits, uint32_t* byp_bits, uint32_t* err,
-                          cudaStream_t st)
+                          cudaStream_t st, uint32_t lanes_req)
 {
     if (n_streams == 0) return 0;
-    const uint32_t lanes = lanes_per_stream(n_streams);
+    const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
     encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
         idx_planar, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_slots, byp_slots,
         slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err, lanes);
@@ -191,10 +192,10 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, const uint8_t* bac_base, const uint64_t* bac_off,
                           const uint32_t* bac_bits, const uint8_t* byp_base, const uint64_t* byp_off,
-                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st)
+                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st, uint32_t lanes_req)
 {
     if (n_streams == 0) return 0;
-    const uint32_t lanes = lanes_per_stream(n_streams);
+    const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
     decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
         idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off,
         bac_bits, byp_base, byp_off, byp_bits, err, lanes);

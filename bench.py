@@ -45,10 +45,12 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=24, help='images per GPU per step')
     ap.add_argument('--height', type=int, default=512)
     ap.add_argument('--width', type=int, default=768)
-    ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'fp32'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--cpu-sample', type=int, default=0, help='images in the CPU sample (0 = one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '4')),
+    ap.add_argument('--coder-lanes', type=int, default=4,
+                    help='GPU threads per coded stream (0 = one warp per stream: lowest latency)')
+    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '8')),
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')
     return ap.parse_args()
 
@@ -189,8 +191,9 @@ class Slot(object):
     Consecutive steps go to consecutive slots, so that the latency-bound lossless coder of one batch
     overlaps with the tensor-bound transforms of the next ones (classic multi-stream pipelining)."""
 
-    def __init__(self, lib, native, native_codec, weights, math, device, n, h, w, bound, world):
+    def __init__(self, lib, native, native_codec, weights, math, device, n, h, w, bound, world, coder_lanes):
         self.codec = native_codec.Codec(weights, False, device=device, math=math, own_stream=True)
+        self.codec.set_coder_lanes(coder_lanes)
         self.stream = self.codec.stream
         self.d_container = lib.eae_device_alloc(bound)
         self.d_recon = lib.eae_device_alloc(n*h*w)
@@ -238,7 +241,7 @@ def run_gpu_arm(args):
     native_params = params.native()
     bound = int(lib.eae_container_bound(n, h, w, params.truncated_unary_length))
     depth = max(1, args.depth)
-    slots = [Slot(lib, _native, native_codec, weights, args.math, local_rank, n, h, w, bound, world)
+    slots = [Slot(lib, _native, native_codec, weights, args.math, local_rank, n, h, w, bound, world, args.coder_lanes)
              for _ in range(depth)]
 
     # Inputs rotate over enough distinct batches to exceed the L2 (each step also streams ~0.7 GB of
@@ -370,7 +373,7 @@ def run_gpu_arm(args):
         'dtype': 'f32' if args.math == 'fp32' else args.math,
         'data': 'synthetic',
         'config': {'workload': workload_name(args), 'batch_per_gpu': n, 'math': args.math,
-                   'pipeline_depth': depth,
+                   'pipeline_depth': depth, 'coder_lanes': args.coder_lanes,
                    'pipelining': 'consecutive steps run on {} CUDA streams (one codec + workspace each), so the '
                                  'latency-bound coder of one batch overlaps the transforms of the next'.format(depth),
                    'l2': 'inputs rotate over {} distinct batches ({} MB > 126 MB L2); every step also streams about '

@@ -256,6 +256,10 @@ int eae_codec_create(eae_codec_t** codec, const eae_weights_t* weights, int are_
 int eae_codec_destroy(eae_codec_t* codec);
 int eae_codec_set_math(eae_codec_t* codec, int math_mode);
 int eae_codec_get_math(const eae_codec_t* codec);
+/* GPU threads per coded stream in the fused pipeline: 0 (default) = one warp per stream while they fit, the
+ * lowest batch latency; 1, 2 or 4 pack 32, 16 or 8 streams per warp, which costs latency but far fewer issue
+ * slots — the choice when batches are pipelined on several CUDA streams. */
+int eae_codec_set_coder_lanes(eae_codec_t* codec, uint32_t lanes);
 
 /* Replaces eae.batching.encode_mini_batches' sess.run(node_y) (eae/batching.py:56-100,
  * eae/graph/components.py:86-142): uint8 [n, h, w, 1] -> float32 [n, h/16, w/16, 128]. */
