@@ -37,8 +37,11 @@ struct eae_codec {
 
     // ---- coder workspace ----
     uint32_t cw_streams = 0, cw_size = 0, cw_L = 0, cw_slot = 0;
-    DevBuf idx_planar, bac_slots, byp_slots, bac_bits, byp_bits, err, bac_off, byp_off, total_bytes;
+    DevBuf idx_planar, bac_slots, byp_slots, bac_bits, byp_bits, err, bac_off, byp_off, total_bytes, enc_scratch;
     DevBuf table, mean, delta, flag, stats;
+    DevBuf qtable, row_flags;          // coder v3: fixed-point multipliers + per-row validity (prepare_table_kernel)
+    std::vector<double> table_host;    // the table the device copies were made from
+    std::vector<float> delta_host, mean_host;
     uint64_t last_idx_elems = 0;
 };
 
@@ -114,6 +117,7 @@ int ensure_coder(eae_codec* c, uint32_t n_streams, uint32_t size, uint32_t L)
     EAE_TRY(c->err.alloc((size_t)n_streams * 4));
     EAE_TRY(c->bac_off.alloc((size_t)n_streams * 8));
     EAE_TRY(c->byp_off.alloc((size_t)n_streams * 8));
+    EAE_TRY(c->enc_scratch.alloc(coder_encode_scratch_bytes(n_streams, size, L)));
     if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
     if (!c->flag.p) EAE_TRY(c->flag.alloc(8));   // [0] bit flags, [1] first coder error
     if (!c->stats.p) EAE_TRY(c->stats.alloc(sizeof(eae_batch_stats_t)));
@@ -129,13 +133,33 @@ int upload_params(eae_codec* c, const eae_coding_params_t* prm, cudaStream_t st)
     if (L > 255) { set_error("truncated unary length %u exceeds 255", L); return EAE_ERR_ARGUMENT; }
     for (int i = 0; i < EAE_NB_MAPS; i++)
         if (!(prm->bin_widths[i] > 0.f)) { set_error("A quantization bin width is not strictly positive."); return EAE_ERR_ARGUMENT; }
-    if (c->table.bytes < (size_t)EAE_NB_MAPS * L * 8) EAE_TRY(c->table.alloc((size_t)EAE_NB_MAPS * L * 8));
+    // The parameters rarely change between calls: upload (and re-derive the coder's fixed-point table) only
+    // when they differ from what the device already holds.
+    const size_t n_tab = (size_t)EAE_NB_MAPS * L;
+    if (c->table_host.size() != n_tab || memcmp(c->table_host.data(), prm->table, n_tab * 8) != 0) {
+        if (c->table.bytes < n_tab * 8) {
+            EAE_TRY(c->table.alloc(n_tab * 8));
+            EAE_TRY(c->qtable.alloc(n_tab * 8));
+        }
+        if (!c->row_flags.p) EAE_TRY(c->row_flags.alloc(EAE_NB_MAPS));
+        c->table_host.assign(prm->table, prm->table + n_tab);
+        // pageable source: the copy is staged before the call returns, so the vector may change afterwards
+        EAE_CUDA_OK(cudaMemcpyAsync(c->table.p, c->table_host.data(), n_tab * 8, cudaMemcpyHostToDevice, st));
+        EAE_TRY(launch_prepare_table(c->table.as<double>(), EAE_NB_MAPS, L, c->qtable.as<uint64_t>(),
+                                     c->row_flags.as<uint8_t>(), st));
+    }
     if (!c->mean.p) EAE_TRY(c->mean.alloc(EAE_NB_MAPS * 4));
     if (!c->delta.p) EAE_TRY(c->delta.alloc(EAE_NB_MAPS * 4));
-    EAE_CUDA_OK(cudaMemcpyAsync(c->table.p, prm->table, (size_t)EAE_NB_MAPS * L * 8, cudaMemcpyHostToDevice, st));
-    EAE_CUDA_OK(cudaMemcpyAsync(c->delta.p, prm->bin_widths, EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
-    if (prm->map_mean) EAE_CUDA_OK(cudaMemcpyAsync(c->mean.p, prm->map_mean, EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
-    else EAE_CUDA_OK(cudaMemsetAsync(c->mean.p, 0, EAE_NB_MAPS * 4, st));
+    if (c->delta_host.size() != EAE_NB_MAPS || memcmp(c->delta_host.data(), prm->bin_widths, EAE_NB_MAPS * 4) != 0) {
+        c->delta_host.assign(prm->bin_widths, prm->bin_widths + EAE_NB_MAPS);
+        EAE_CUDA_OK(cudaMemcpyAsync(c->delta.p, c->delta_host.data(), EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<float> mean(EAE_NB_MAPS, 0.f);
+    if (prm->map_mean) mean.assign(prm->map_mean, prm->map_mean + EAE_NB_MAPS);
+    if (c->mean_host != mean) {
+        c->mean_host = mean;
+        EAE_CUDA_OK(cudaMemcpyAsync(c->mean.p, c->mean_host.data(), EAE_NB_MAPS * 4, cudaMemcpyHostToDevice, st));
+    }
     return 0;
 }
 
@@ -428,7 +452,8 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
         EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
                                       c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st,
-                                      c->coder_lanes));
+                                      c->coder_lanes, c->enc_scratch.p, c->qtable.as<uint64_t>(),
+                                      c->row_flags.as<uint8_t>()));
     }
     ProfScope prof_pack(kProfPack, st);
     stream_offsets_kernel<<<1, 1024, 0, st>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
@@ -479,7 +504,8 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
         EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
                                       container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
-                                      c->err.as<uint32_t>(), st, c->coder_lanes));
+                                      c->err.as<uint32_t>(), st, c->coder_lanes, c->qtable.as<uint64_t>(),
+                                      c->row_flags.as<uint8_t>()));
     }
     c->last_idx_elems = (uint64_t)n_streams * hw3;
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {

@@ -70,6 +70,409 @@ decode_streams_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t si
     err[s] = core::decode_stream(out + (size_t)s * size, size, table + (size_t)row * L, L, bac, byp);
 }
 
+// =================================================================================================
+// Coder v2 (default): the lean formulation of coder_core.cuh.
+//
+//   encode = binarize_streams_kernel (parallel: one warp per stream writes the truncated-unary bit string
+//            of the stream and its complete bypass stream)
+//          + encode_streams2_kernel  (sequential: one thread per stream, one branch-light step per bin)
+//   decode = decode_streams2_kernel  (one thread per stream: arithmetic decoding of all prefixes, then the
+//            bypass pass over the same symbols)
+//
+// Version 1 spent ~50 instructions per bin in a warp that carried ONE stream (31 idle lanes), or diverged
+// on every symbol boundary / flush / E3 loop when 32 streams shared a warp. Here the per-bin step has no
+// data-dependent loop and no symbol logic, so the streams of a warp stay converged and the kernel needs
+// ~1/30 of the issue slots: it is bounded by the dependent chain of one step (~100-150 cycles) times the
+// number of bins of the longest stream, and leaves the SMs free for the transforms of other batches.
+//
+// Streams that share a warp are chosen to be the SAME feature map of different images (similar statistics,
+// hence similar bin counts): slot j -> stream (j % group) * table_rows + j / group.
+__global__ void __launch_bounds__(128)
+binarize_streams_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint32_t size,
+                        uint32_t table_rows, uint32_t L, const uint8_t* __restrict__ skip_mask,
+                        uint32_t* __restrict__ nbins, uint32_t* __restrict__ ubits, uint32_t uwords,
+                        uint8_t* __restrict__ byp_slots, uint32_t slot_bytes, uint32_t* __restrict__ byp_bits)
+{
+    extern __shared__ uint32_t bin_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ub_words = L + 2u;          // 32 symbols x L bins + a carried partial word
+    uint32_t* ub = bin_smem + warp * (ub_words + 34u);
+    uint32_t* bb = ub + ub_words;              // 32 symbols x 32 bypass bits + a carried partial word
+    const uint32_t s = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (s >= n_streams) return;
+    if (skip_mask && skip_mask[s % table_rows]) {
+        if (lane == 0) { nbins[s] = 0; byp_bits[s] = 0; }
+        return;
+    }
+    for (uint32_t j = lane; j < ub_words; j += 32) ub[j] = 0;
+    for (uint32_t j = lane; j < 34u; j += 32) bb[j] = 0;
+    __syncwarp();
+    const int16_t* src = idx + (size_t)s * size;
+    uint32_t* uout = ubits + (size_t)s * uwords;
+    uint32_t* bout = reinterpret_cast<uint32_t*>(byp_slots + (size_t)s * slot_bytes);
+    uint32_t ucarry = 0, bcarry = 0;           // bits waiting in word 0 of the staging buffers
+    uint32_t uw_out = 0, bw_out = 0;           // whole words written so far
+    uint32_t total_bins = 0, total_byp = 0;
+    for (uint32_t base = 0; base < size; base += 32) {
+        const uint32_t i = base + lane;
+        const bool have = i < size;
+        const int v = have ? (int)__ldg(src + i) : 0;
+        const uint32_t a = (uint32_t)(v < 0 ? -v : v);
+        const uint32_t ones = have ? (a < L ? a : L) : 0u;
+        const uint32_t nb = have ? ones + (a < L ? 1u : 0u) : 0u;
+        uint32_t code = 0, cnt = 0;
+        if (have) core::bypass_code(v, a, L, code, cnt);
+        uint32_t un = nb, bn = cnt;            // inclusive scans over the warp
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tu = __shfl_up_sync(0xFFFFFFFFu, un, o), tb = __shfl_up_sync(0xFFFFFFFFu, bn, o);
+            if ((int)lane >= o) { un += tu; bn += tb; }
+        }
+        const uint32_t utot = __shfl_sync(0xFFFFFFFFu, un, 31), btot = __shfl_sync(0xFFFFFFFFu, bn, 31);
+        {   // `ones` one-bits from this symbol's first bin; its terminating zero is already there
+            uint32_t pos = ucarry + un - nb, rem = ones;
+            while (rem) {
+                const uint32_t b = pos & 31u, c = (32u - b) < rem ? (32u - b) : rem;
+                atomicOr(&ub[pos >> 5], (c == 32u ? 0xFFFFFFFFu : ((1u << c) - 1u)) << b);
+                pos += c; rem -= c;
+            }
+        }
+        if (cnt) {
+            const uint32_t pos = bcarry + bn - cnt, b = pos & 31u;
+            atomicOr(&bb[pos >> 5], code << b);
+            if (b + cnt > 32u) atomicOr(&bb[(pos >> 5) + 1u], code >> (32u - b));
+        }
+        __syncwarp();
+        const uint32_t ubits_now = ucarry + utot, ufull = ubits_now >> 5;
+        const uint32_t bbits_now = bcarry + btot, bfull = bbits_now >> 5;
+        for (uint32_t j = lane; j < ufull; j += 32) uout[uw_out + j] = ub[j];
+        for (uint32_t j = lane; j < bfull; j += 32) bout[bw_out + j] = bb[j];
+        const uint32_t ulast = ub[ufull], blast = bb[bfull];
+        __syncwarp();
+        for (uint32_t j = lane; j <= ufull; j += 32) ub[j] = 0;
+        for (uint32_t j = lane; j <= bfull; j += 32) bb[j] = 0;
+        __syncwarp();
+        if (lane == 0) { ub[0] = ulast; bb[0] = blast; }
+        __syncwarp();
+        uw_out += ufull; ucarry = ubits_now & 31u;
+        bw_out += bfull; bcarry = bbits_now & 31u;
+        total_bins += utot; total_byp += btot;
+    }
+    if (lane == 0) {
+        if (ucarry) uout[uw_out] = ub[0];
+        if (bcarry) bout[bw_out] = bb[0];
+        nbins[s] = total_bins;
+        byp_bits[s] = total_byp;
+    }
+}
+
+__device__ __forceinline__ uint32_t slot_to_stream(uint32_t j, uint32_t group, uint32_t table_rows)
+{
+    return group ? (j % group) * table_rows + j / group : j;
+}
+
+__global__ void __launch_bounds__(64)
+encode_streams2_kernel(const uint32_t* __restrict__ nbins, const uint32_t* __restrict__ ubits, uint32_t uwords,
+                       uint32_t n_streams, const double* __restrict__ table, uint32_t table_rows, uint32_t L,
+                       const uint8_t* __restrict__ skip_mask, uint8_t* __restrict__ bac_slots,
+                       uint32_t slot_bytes, uint32_t cap_bits, uint32_t* __restrict__ bac_bits,
+                       uint32_t* __restrict__ err, uint32_t lanes, uint32_t group)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t j = t / lanes;
+    if (j >= n_streams) return;
+    const uint32_t s = slot_to_stream(j, group, table_rows);
+    const uint32_t row = s % table_rows;
+    if (skip_mask && skip_mask[row]) { bac_bits[s] = 0; err[s] = 0; return; }
+    const double* prow = table + (size_t)row * L;
+    const uint32_t* uw = ubits + (size_t)s * uwords;
+    const uint32_t nb = nbins[s];
+    core::BitSink bac;
+    bac.init(bac_slots + (size_t)s * slot_bytes, cap_bits);
+    core::BacState st = {0u, core::kRangeMax, 0u};
+    uint32_t e = 0, k = 0, w = 0, wnext = nb ? __ldg(uw) : 0u;
+    double p = __ldg(prow);
+    for (uint32_t g = 0; g < nb; g++) {
+        if ((g & 31u) == 0u) {                 // same g for every lane: converged
+            w = wnext;
+            if (g + 32u < nb) wnext = __ldg(uw + (g >> 5) + 1u);
+        }
+        const uint32_t bit = (w >> (g & 31u)) & 1u;
+        k = (bit && k + 1u < L) ? k + 1u : 0u;
+        const double p_next = __ldg(prow + k);  // off the dependent chain of the step below
+        e = core::lean_encode_bin(st, bac, bit, p);
+        if (e) break;
+        p = p_next;
+    }
+    if (!e) e = core::bac_finish(st, bac);
+    bac.flush();
+    bac_bits[s] = bac.nbits;
+    err[s] = e;
+}
+
+__global__ void __launch_bounds__(64)
+decode_streams2_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
+                       const double* __restrict__ table, uint32_t table_rows, uint32_t L,
+                       const uint8_t* __restrict__ skip_mask, const uint8_t* __restrict__ bac_base,
+                       const uint64_t* __restrict__ bac_off, const uint32_t* __restrict__ bac_bits,
+                       const uint8_t* __restrict__ byp_base, const uint64_t* __restrict__ byp_off,
+                       const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err, uint32_t lanes,
+                       uint32_t group)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t j = t / lanes;
+    if (j >= n_streams) return;
+    const uint32_t s = slot_to_stream(j, group, table_rows);
+    const uint32_t row = s % table_rows;
+    if (skip_mask && skip_mask[row]) { err[s] = 0; return; }
+    const double* prow = table + (size_t)row * L;
+    int16_t* dst = out + (size_t)s * size;
+    core::BitSource bac;
+    bac.init(bac_base + bac_off[s], bac_bits[s]);
+    core::DecState st;
+    core::lean_decode_start(st, bac);
+    // phase A: the truncated-unary prefix of every symbol
+    uint32_t e = 0, n_ok = size, i = 0, a = 0, k = 0;
+    const double p0 = __ldg(prow);
+    double p = p0;
+    while (i < size) {
+        if (!(p > 0.0 && p < 1.0)) { e = core::kErrProbability; n_ok = i; break; }
+        // the next probability is p[0] (symbol finished) or p[k + 1]: fetch the latter before the bit is known
+        const double p_up = __ldg(prow + (k + 1u < L ? k + 1u : k));
+        const uint32_t bit = core::lean_decode_bin(st, bac, p);
+        a += bit;
+        const bool done = !bit || k == L - 1u;
+        if (done) { dst[i] = (int16_t)a; i++; a = 0; }
+        k = done ? 0u : k + 1u;
+        p = done ? p0 : p_up;
+    }
+    // phase B: EG0 suffixes and signs from the bypass stream
+    core::BitSource byp;
+    byp.init(byp_base + byp_off[s], byp_bits[s]);
+    for (i = 0; i < n_ok; i++) {
+        const uint32_t a0 = (uint32_t)(uint16_t)dst[i];
+        if (a0 == 0u) continue;
+        int v;
+        const uint32_t eb = core::lean_decode_bypass(a0, L, byp, v);
+        if (eb) { e = eb; break; }
+        dst[i] = (int16_t)v;
+    }
+    err[s] = e;
+}
+
+// =================================================================================================
+// Coder v3 (default): the same two passes with the branch-free step of coder_core.cuh ("fast formulation").
+// Per table row, `row_flags` says whether every probability is valid (bit 0: the loop then needs no error
+// test at all) and whether the 48-bit fixed-point multipliers in `qtable` reproduce floor(p * range) for every
+// range (bit 1, established exhaustively by prepare_table_kernel): rows without bit 0 take the lean loop,
+// rows without bit 1 the FP64 multiply. Without a prepared table (row_flags == NULL) validity is checked
+// here and the multiply is FP64.
+__global__ void __launch_bounds__(256)
+prepare_table_kernel(const double* __restrict__ table, uint32_t L, uint64_t* __restrict__ qtable,
+                     uint8_t* __restrict__ row_flags)
+{
+    __shared__ uint32_t bad_p, bad_q;
+    const uint32_t row = blockIdx.x;
+    if (threadIdx.x == 0) { bad_p = 0; bad_q = 0; }
+    __syncthreads();
+    const double* prow = table + (size_t)row * L;
+    for (uint32_t j = 0; j < L; j++) {
+        const double p = prow[j];
+        const bool ok = p > 0.0 && p < 1.0;
+        const core::MulFp64 a{p};
+        const core::MulFixed48 b{core::fixed48_of(p)};
+        if (threadIdx.x == 0) { qtable[(size_t)row * L + j] = b.q; if (!ok) bad_p = 1; }
+        if (!ok) continue;
+        uint32_t diff = 0;
+        for (uint32_t r = threadIdx.x; r <= 0xFFFFu; r += blockDim.x) diff |= a(r) ^ b(r);
+        if (diff) bad_q = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) row_flags[row] = (uint8_t)((bad_p ? 0u : 1u) | ((bad_p || bad_q) ? 0u : 2u));
+}
+
+__device__ __forceinline__ bool row_is_valid(const double* prow, uint32_t L)
+{
+    bool ok = true;
+    for (uint32_t j = 0; j < L; j++) { const double p = __ldg(prow + j); ok = ok && p > 0.0 && p < 1.0; }
+    return ok;
+}
+
+template <typename Mul, typename T>
+__device__ __forceinline__ void encode_bins_fast(const T* __restrict__ mrow, const uint32_t* __restrict__ uw,
+                                                 uint32_t nb, uint32_t L, core::BacState& st, core::FastSink& bac)
+{
+    uint32_t k = 0, w = 0, wnext = nb ? __ldg(uw) : 0u;
+    Mul mul{__ldg(mrow)};
+    #pragma unroll 2
+    for (uint32_t g = 0; g < nb; g++) {
+        if ((g & 31u) == 0u) {                 // same g in every lane: converged
+            w = wnext;
+            if (g + 32u < nb) wnext = __ldg(uw + (g >> 5) + 1u);
+        }
+        const uint32_t bit = w & 1u;
+        w >>= 1;
+        k = (bit && k + 1u < L) ? k + 1u : 0u;
+        const Mul next{__ldg(mrow + k)};         // off the dependent chain of the step
+        core::fast_encode_bin(st, bac, bit, mul);
+        mul = next;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+encode_streams3_kernel(const uint32_t* __restrict__ nbins, const uint32_t* __restrict__ ubits, uint32_t uwords,
+                       uint32_t n_streams, const double* __restrict__ table, const uint64_t* __restrict__ qtable,
+                       const uint8_t* __restrict__ row_flags, uint32_t table_rows, uint32_t L,
+                       const uint8_t* __restrict__ skip_mask, uint8_t* __restrict__ bac_slots,
+                       uint32_t slot_bytes, uint32_t cap_bits, uint32_t* __restrict__ bac_bits,
+                       uint32_t* __restrict__ err, uint32_t lanes, uint32_t group)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t j = t / lanes;
+    if (j >= n_streams) return;
+    const uint32_t s = slot_to_stream(j, group, table_rows);
+    const uint32_t row = s % table_rows;
+    if (skip_mask && skip_mask[row]) { bac_bits[s] = 0; err[s] = 0; return; }
+    const double* prow = table + (size_t)row * L;
+    const uint32_t* uw = ubits + (size_t)s * uwords;
+    const uint32_t nb = nbins[s];
+    uint8_t* slot = bac_slots + (size_t)s * slot_bytes;
+    const uint32_t flags = row_flags ? row_flags[row] : (row_is_valid(prow, L) ? 1u : 0u);
+    core::BacState st = {0u, core::kRangeMax, 0u};
+    if (!(flags & 1u)) {
+        // a probability outside (0, 1): the lean loop reports errors in the reference's order
+        core::BitSink bac;
+        bac.init(slot, cap_bits);
+        uint32_t e = 0, k = 0;
+        for (uint32_t g = 0; g < nb && !e; g++) {
+            const uint32_t bit = (__ldg(uw + (g >> 5)) >> (g & 31u)) & 1u;
+            e = core::lean_encode_bin(st, bac, bit, __ldg(prow + k));
+            k = (bit && k + 1u < L) ? k + 1u : 0u;
+        }
+        if (!e) e = core::bac_finish(st, bac);
+        bac.flush();
+        bac_bits[s] = bac.nbits;
+        err[s] = e;
+        return;
+    }
+    core::FastSink bac;
+    bac.init(slot, cap_bits);
+    if (flags & 2u) encode_bins_fast<core::MulFixed48>(qtable + (size_t)row * L, uw, nb, L, st, bac);
+    else encode_bins_fast<core::MulFp64>(prow, uw, nb, L, st, bac);
+    core::fast_finish(st, bac);
+    bac.flush();
+    bac_bits[s] = bac.pos;
+    err[s] = bac.pos > cap_bits ? core::kErrCapacity : 0u;
+}
+
+template <typename Mul, typename T>
+__device__ __forceinline__ void decode_prefixes_fast(const T* __restrict__ mrow, uint32_t L, uint32_t size,
+                                                     core::FastSource& bac, int16_t* __restrict__ dst)
+{
+    core::DecState st;
+    core::fast_decode_start(st, bac);
+    uint32_t i = 0, a = 0, k = 0;
+    const Mul m0{__ldg(mrow)};
+    Mul mul = m0;
+    while (i < size) {
+        // the next multiplier is entry 0 (symbol finished) or entry k + 1: fetch the latter before the bit is known
+        const Mul up{__ldg(mrow + (k + 1u < L ? k + 1u : k))};
+        const uint32_t bit = core::fast_decode_bin(st, bac, mul);
+        a += bit;
+        const bool done = !bit || k == L - 1u;
+        if (done) { dst[i] = (int16_t)a; i++; a = 0; }
+        k = done ? 0u : k + 1u;
+        mul = done ? m0 : up;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+decode_streams3_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
+                       const double* __restrict__ table, const uint64_t* __restrict__ qtable,
+                       const uint8_t* __restrict__ row_flags, uint32_t table_rows, uint32_t L,
+                       const uint8_t* __restrict__ skip_mask, const uint8_t* __restrict__ bac_base,
+                       const uint64_t* __restrict__ bac_off, const uint32_t* __restrict__ bac_bits,
+                       const uint8_t* __restrict__ byp_base, const uint64_t* __restrict__ byp_off,
+                       const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err, uint32_t lanes,
+                       uint32_t group)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t % lanes) return;
+    const uint32_t j = t / lanes;
+    if (j >= n_streams) return;
+    const uint32_t s = slot_to_stream(j, group, table_rows);
+    const uint32_t row = s % table_rows;
+    if (skip_mask && skip_mask[row]) { err[s] = 0; return; }
+    const double* prow = table + (size_t)row * L;
+    int16_t* dst = out + (size_t)s * size;
+    const uint32_t flags = row_flags ? row_flags[row] : (row_is_valid(prow, L) ? 1u : 0u);
+    uint32_t e = 0, n_ok = size;
+    // phase A: the truncated-unary prefix of every symbol
+    if (!(flags & 1u)) {
+        core::BitSource bac;
+        bac.init(bac_base + bac_off[s], bac_bits[s]);
+        core::DecState st;
+        core::lean_decode_start(st, bac);
+        uint32_t i = 0, a = 0, k = 0;
+        while (i < size) {
+            const double p = __ldg(prow + k);
+            if (!(p > 0.0 && p < 1.0)) { e = core::kErrProbability; n_ok = i; break; }
+            const uint32_t bit = core::lean_decode_bin(st, bac, p);
+            a += bit;
+            const bool done = !bit || k == L - 1u;
+            if (done) { dst[i] = (int16_t)a; i++; a = 0; }
+            k = done ? 0u : k + 1u;
+        }
+    } else {
+        core::FastSource bac;
+        bac.init(bac_base + bac_off[s], bac_bits[s]);
+        if (flags & 2u) decode_prefixes_fast<core::MulFixed48>(qtable + (size_t)row * L, L, size, bac, dst);
+        else decode_prefixes_fast<core::MulFp64>(prow, L, size, bac, dst);
+    }
+    // phase B: EG0 suffixes and signs from the bypass stream
+    core::BitSource byp;
+    byp.init(byp_base + byp_off[s], byp_bits[s]);
+    for (uint32_t i = 0; i < n_ok; i++) {
+        const uint32_t a0 = (uint32_t)(uint16_t)dst[i];
+        if (a0 == 0u) continue;
+        int v;
+        const uint32_t eb = core::lean_decode_bypass(a0, L, byp, v);
+        if (eb) { e = eb; break; }
+        dst[i] = (int16_t)v;
+    }
+    err[s] = e;
+}
+
+int coder_version()
+{
+    static int v = 0;
+    if (!v) {
+        const char* env = getenv("EAE_CODER_VERSION");
+        v = env ? atoi(env) : 3;
+        if (v < 1 || v > 3) v = 3;
+    }
+    return v;
+}
+
+// Threads per stream slot of the version-2 kernels (only the first thread of a slot works): as few warps as
+// keep about one warp per SM sub-partition busy, so that a small batch still spreads over the whole GPU.
+inline uint32_t lanes_v2(uint32_t n_streams, uint32_t requested)
+{
+    static int forced = -1;
+    if (forced < 0) {
+        const char* env = getenv("EAE_CODER_LANES");
+        forced = env ? atoi(env) : 0;
+    }
+    if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return (uint32_t)forced;
+    if (requested >= 1 && requested <= 32 && (requested & (requested - 1)) == 0) return requested;
+    uint32_t lanes = 32;
+    while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 4ull) lanes >>= 1;
+    return lanes;
+}
+
 // Threads per stream: one warp per stream until that would exceed ~32 warps per SM, then halve.
 inline uint32_t lanes_per_stream(uint32_t n_streams, uint32_t requested)
 {
@@ -173,18 +576,57 @@ uint32_t coder_capacity_bits(uint32_t size, uint32_t L)
     return r ? bits + 8u - r : bits;
 }
 
+size_t coder_encode_scratch_bytes(uint32_t n_streams, uint32_t size, uint32_t L)
+{
+    // per stream: the truncated-unary bit string (at most L bins per symbol) in whole words, + the bin count
+    const size_t uwords = ((size_t)size * L + 31) / 32 + 1;
+    return ((size_t)n_streams * (uwords + 1) * 4 + 255) & ~(size_t)255;
+}
+
 int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_t size,
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, uint8_t* bac_slots, uint8_t* byp_slots,
                           uint32_t slot_bytes, uint32_t* bac_bits, uint32_t* byp_bits, uint32_t* err,
-                          cudaStream_t st, uint32_t lanes_req)
+                          cudaStream_t st, uint32_t lanes_req, void* scratch, const uint64_t* qtable_dev,
+                          const uint8_t* row_flags_dev)
 {
     if (n_streams == 0) return 0;
-    const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
-    encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
-        idx_planar, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_slots, byp_slots,
-        slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err, lanes);
+    if (coder_version() == 1) {
+        const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
+        encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
+            idx_planar, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_slots, byp_slots,
+            slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err, lanes);
+        EAE_LAUNCH_OK();
+        return 0;
+    }
+    void* own = nullptr;
+    if (!scratch) {     // callers without a persistent workspace (C-ABI stream entry points)
+        EAE_CUDA_OK(cudaMallocAsync(&own, coder_encode_scratch_bytes(n_streams, size, L), st));
+        scratch = own;
+    }
+    const uint32_t uwords = (uint32_t)(((size_t)size * L + 31) / 32 + 1);
+    uint32_t* nbins = reinterpret_cast<uint32_t*>(scratch);
+    uint32_t* ubits = nbins + n_streams;
+    const uint32_t warps = 4;
+    const size_t smem = (size_t)warps * (L + 2u + 34u) * 4;
+    binarize_streams_kernel<<<ceil_div_u32(n_streams, warps), warps * 32, smem, st>>>(
+        idx_planar, n_streams, size, table_rows, L, skip_mask_dev, nbins, ubits, uwords, byp_slots, slot_bytes,
+        byp_bits);
     EAE_LAUNCH_OK();
+    const uint32_t lanes = lanes_v2(n_streams, lanes_req);
+    const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
+    const uint64_t threads = (uint64_t)n_streams * lanes;
+    const uint32_t block = threads <= 148ull * 4ull * 32ull ? 32u : 64u;   // few warps: one per CTA, spread over the SMs
+    if (coder_version() == 2)
+        encode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+            nbins, ubits, uwords, n_streams, table_dev, table_rows, L, skip_mask_dev, bac_slots, slot_bytes,
+            coder_capacity_bits(size, L), bac_bits, err, lanes, group);
+    else
+        encode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+            nbins, ubits, uwords, n_streams, table_dev, qtable_dev, qtable_dev ? row_flags_dev : nullptr, table_rows, L,
+            skip_mask_dev, bac_slots, slot_bytes, coder_capacity_bits(size, L), bac_bits, err, lanes, group);
+    EAE_LAUNCH_OK();
+    if (own) EAE_CUDA_OK(cudaFreeAsync(own, st));
     return 0;
 }
 
@@ -192,13 +634,39 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, const uint8_t* bac_base, const uint64_t* bac_off,
                           const uint32_t* bac_bits, const uint8_t* byp_base, const uint64_t* byp_off,
-                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st, uint32_t lanes_req)
+                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st, uint32_t lanes_req,
+                          const uint64_t* qtable_dev, const uint8_t* row_flags_dev)
 {
     if (n_streams == 0) return 0;
-    const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
-    decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
-        idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off,
-        bac_bits, byp_base, byp_off, byp_bits, err, lanes);
+    if (coder_version() == 1) {
+        const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
+        decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
+            idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off,
+            bac_bits, byp_base, byp_off, byp_bits, err, lanes);
+        EAE_LAUNCH_OK();
+        return 0;
+    }
+    const uint32_t lanes = lanes_v2(n_streams, lanes_req);
+    const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
+    const uint64_t threads = (uint64_t)n_streams * lanes;
+    const uint32_t block = threads <= 148ull * 4ull * 32ull ? 32u : 64u;
+    if (coder_version() == 2)
+        decode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+            idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off, bac_bits,
+            byp_base, byp_off, byp_bits, err, lanes, group);
+    else
+        decode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+            idx_planar_out, n_streams, size, table_dev, qtable_dev, qtable_dev ? row_flags_dev : nullptr, table_rows, L,
+            skip_mask_dev, bac_base, bac_off, bac_bits, byp_base, byp_off, byp_bits, err, lanes, group);
+    EAE_LAUNCH_OK();
+    return 0;
+}
+
+int launch_prepare_table(const double* table_dev, uint32_t rows, uint32_t L, uint64_t* qtable_dev,
+                         uint8_t* row_flags_dev, cudaStream_t st)
+{
+    if (rows == 0) return 0;
+    prepare_table_kernel<<<rows, 256, 0, st>>>(table_dev, L, qtable_dev, row_flags_dev);
     EAE_LAUNCH_OK();
     return 0;
 }

@@ -11,12 +11,19 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, uint8_t* bac_slots, uint8_t* byp_slots,
                           uint32_t slot_bytes, uint32_t* bac_bits, uint32_t* byp_bits, uint32_t* err,
-                          cudaStream_t st, uint32_t lanes = 0);
+                          cudaStream_t st, uint32_t lanes = 0, void* scratch = nullptr,
+                          const uint64_t* qtable_dev = nullptr, const uint8_t* row_flags_dev = nullptr);
+// Bytes of `scratch` (truncated-unary bit strings + bin counts); NULL scratch = stream-ordered allocation.
+size_t coder_encode_scratch_bytes(uint32_t n_streams, uint32_t size, uint32_t L);
 int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t size,
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, const uint8_t* bac_base, const uint64_t* bac_off,
                           const uint32_t* bac_bits, const uint8_t* byp_base, const uint64_t* byp_off,
-                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st, uint32_t lanes = 0);
+                          const uint32_t* byp_bits, uint32_t* err, cudaStream_t st, uint32_t lanes = 0,
+                          const uint64_t* qtable_dev = nullptr, const uint8_t* row_flags_dev = nullptr);
+// Fixed-point multipliers and validity flags of a probability table (coder v3); see prepare_table_kernel.
+int launch_prepare_table(const double* table_dev, uint32_t rows, uint32_t L, uint64_t* qtable_dev,
+                         uint8_t* row_flags_dev, cudaStream_t st);
 int launch_slot_offsets(uint64_t* off, uint32_t n, uint32_t slot_bytes, cudaStream_t st);
 int launch_transpose_i16(const int16_t* in, int16_t* out, uint32_t batch, uint32_t rows, uint32_t cols,
                          cudaStream_t st);

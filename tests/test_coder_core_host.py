@@ -21,12 +21,35 @@ LIB = os.path.join(HERE, 'host_harness', 'libcoder_core_harness.so')
 def harness():
     newest = max(os.path.getmtime(SRC), os.path.getmtime(CORE))
     if not os.path.isfile(LIB) or os.path.getmtime(LIB) < newest:
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off', '-x', 'c++', SRC,
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off', '-x', 'c++', SRC,
                                '-o', LIB])
     lib = ctypes.CDLL(LIB)
-    lib.harness_encode.restype = ctypes.c_int
-    lib.harness_decode.restype = ctypes.c_int
+    for name in ('harness_encode', 'harness_decode', 'harness_encode2', 'harness_decode2', 'harness_encode3',
+                 'harness_decode3'):
+        getattr(lib, name).restype = ctypes.c_int
+    lib.harness_e3_exhaustive.restype = ctypes.c_uint64
+    lib.harness_rescale_exhaustive.restype = ctypes.c_uint64
     return lib
+
+
+class Formulation(object):
+    """`encode` / `decode` entry points of one formulation of the core: 'v1' = flattened one-pass loop,
+    'v2' = lean two-pass form (the kernels' path for table rows with invalid entries), 'v3-fp64' / 'v3-fixed' =
+    the branch-free form the default CUDA kernels instantiate, with the reference's FP64 multiply or the
+    validated 48-bit fixed-point one."""
+
+    def __init__(self, lib, suffix, mode):
+        enc = getattr(lib, 'harness_encode' + suffix)
+        dec = getattr(lib, 'harness_decode' + suffix)
+        extra = () if mode is None else (ctypes.c_int(mode),)
+        self.harness_encode = lambda *a: enc(*(a + extra))
+        self.harness_decode = lambda *a: dec(*(a + extra))
+
+
+@pytest.fixture(scope='module', params=[('', None), ('2', None), ('3', 0), ('3', 1)],
+                ids=['v1', 'v2', 'v3-fp64', 'v3-fixed'])
+def core(request, harness):
+    return Formulation(harness, *request.param)
 
 
 def cap_bits(size, L):
@@ -61,17 +84,17 @@ def decode(lib, size, p, bac, bb, byp, rb, misalign=0):
     return (err, out)
 
 
-def test_known_answers(harness, golden):
+def test_known_answers(core, golden):
     for (name, x, p, bac, byp, bac_bits, byp_bits) in golden.kat_cases():
-        (err, b, bb, r, rb) = encode(harness, x, p)
+        (err, b, bb, r, rb) = encode(core, x, p)
         assert err == 0 and (bb, rb) == (bac_bits, byp_bits), name
         assert numpy.array_equal(b, bac) and numpy.array_equal(r, byp), name
         for mis in range(4):
-            (err, dec) = decode(harness, x.size, p, bac, bac_bits, byp, byp_bits, mis)
+            (err, dec) = decode(core, x.size, p, bac, bac_bits, byp, byp_bits, mis)
             assert err == 0 and numpy.array_equal(dec, x), (name, mis)
 
 
-def test_random_streams_against_the_oracle(harness):
+def test_random_streams_against_the_oracle(core):
     rng = numpy.random.default_rng(17)
     for trial in range(400):
         L = int(rng.integers(1, 41)) if trial % 9 else 255
@@ -83,16 +106,16 @@ def test_random_streams_against_the_oracle(harness):
             x[rng.integers(0, size)] = -32768
             x[rng.integers(0, size)] = 32767
         want = oracle_coder.encode_map(x, p, 'port')
-        got = encode(harness, x, p)
+        got = encode(core, x, p)
         assert got[0] == want[0], (trial, got[0], want[0])
         if want[0] == 0:
             assert (got[2], got[4]) == (want[2], want[4]), trial
             assert numpy.array_equal(got[1], want[1]) and numpy.array_equal(got[3], want[3]), trial
-            (err, dec) = decode(harness, size, p, want[1], want[2], want[3], want[4], trial % 4)
+            (err, dec) = decode(core, size, p, want[1], want[2], want[3], want[4], trial % 4)
             assert err == 0 and numpy.array_equal(dec, x), trial
 
 
-def test_malformed_streams_decode_like_the_oracle(harness):
+def test_malformed_streams_decode_like_the_oracle(core):
     """Truncated / corrupted inputs: same error code and, when both succeed, the same symbols (stale-bit
     padding of BinaryArithmeticCoder.cpp:104-122, 275-315)."""
     rng = numpy.random.default_rng(23)
@@ -114,16 +137,28 @@ def test_malformed_streams_decode_like_the_oracle(harness):
         else:
             bac = rng.integers(0, 256, size=bac.size, dtype=numpy.uint8)
         want = oracle_coder.decode_map(size, p, bac[:(bb + 7)//8], bb, byp[:(rb + 7)//8], rb, 'port')
-        got = decode(harness, size, p, bac[:(bb + 7)//8], bb, byp[:(rb + 7)//8], rb, trial % 3)
+        got = decode(core, size, p, bac[:(bb + 7)//8], bb, byp[:(rb + 7)//8], rb, trial % 3)
         assert got[0] == want[0], (trial, mode, got[0], want[0])
         if want[0] == 0:
             assert numpy.array_equal(got[1], want[1]), (trial, mode)
 
 
-def test_error_codes(harness):
+def test_error_codes(core):
     x = numpy.array([0, 3, -2, 0], dtype=numpy.int16)
     for probs in ([0.5, numpy.nan, 0.5], [0.5, 1.0, 0.5], [0.5, 0.0, 0.5]):
-        assert encode(harness, x, probs)[0] == 4
-    assert encode(harness, numpy.array([0, 1, 0], dtype=numpy.int16), [0.5, 0.5, numpy.nan])[0] == 0
-    assert encode(harness, numpy.array([40], dtype=numpy.int16), numpy.full(40, 0.99))[0] == 1
-    assert encode(harness, numpy.zeros(0, dtype=numpy.int16), [0.5])[0] == 1      # zero-size buffer: capacity error
+        assert encode(core, x, probs)[0] == 4
+    assert encode(core, numpy.array([0, 1, 0], dtype=numpy.int16), [0.5, 0.5, numpy.nan])[0] == 0
+    assert encode(core, numpy.array([40], dtype=numpy.int16), numpy.full(40, 0.99))[0] == 1
+    assert encode(core, numpy.zeros(0, dtype=numpy.int16), [0.5])[0] == 1      # zero-size buffer: capacity error
+
+
+def test_closed_form_e3_matches_the_literal_loop_for_every_register_pair(harness):
+    """e3_steps() and the closed-form register update against the reference's while loop
+    (BinaryArithmeticCoder.cpp:238-246) on all 2^30 pairs low < 0x8000 <= high."""
+    assert harness.harness_e3_exhaustive() == 0
+
+
+def test_combined_rescaling_matches_the_literal_loop_for_every_register_pair(harness):
+    """fast_rescale() (E1/E2 + E3 as one shift, quirk fix-up) against the reference's rescaling loop
+    (BinaryArithmeticCoder.cpp:182-252) on all 2^31 pairs low <= high."""
+    assert harness.harness_rescale_exhaustive() == 0
