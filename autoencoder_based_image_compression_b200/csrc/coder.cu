@@ -300,25 +300,55 @@ __device__ __forceinline__ bool row_is_valid(const double* prow, uint32_t L)
     return ok;
 }
 
+// Fast encoder loop of one stream. The body of the inner loop is one basic block: the bits released by bin
+// g - 1 enter the sink while the interval arithmetic of bin g runs (two independent dependent chains that the
+// scheduler interleaves). Returns the largest number of bits one bin released.
 template <typename Mul, typename T>
-__device__ __forceinline__ void encode_bins_fast(const T* __restrict__ mrow, const uint32_t* __restrict__ uw,
-                                                 uint32_t nb, uint32_t L, core::BacState& st, core::FastSink& bac)
+__device__ __forceinline__ uint32_t encode_bins_fast(const T* __restrict__ mrow, const uint32_t* __restrict__ uw,
+                                                     uint32_t nb, uint32_t L, core::BacState& st, core::FastSink& bac)
 {
-    uint32_t k = 0, w = 0, wnext = nb ? __ldg(uw) : 0u;
+    uint32_t k = 0, ev = 0, ec = 0, worst = 0;
     Mul mul{__ldg(mrow)};
-    #pragma unroll 2
-    for (uint32_t g = 0; g < nb; g++) {
-        if ((g & 31u) == 0u) {                 // same g in every lane: converged
-            w = wnext;
-            if (g + 32u < nb) wnext = __ldg(uw + (g >> 5) + 1u);
+    uint32_t wnext = nb ? __ldg(uw) : 0u;
+    for (uint32_t g0 = 0; g0 < nb; g0 += 32u) {
+        uint32_t w = wnext;
+        if (g0 + 32u < nb) wnext = __ldg(uw + (g0 >> 5) + 1u);
+        const uint32_t cnt = nb - g0 < 32u ? nb - g0 : 32u;
+        #pragma unroll 1
+        for (uint32_t b = 0; b < cnt; b++) {
+            bac.put(ev, ec < 32u ? ec : 0u);
+            const uint32_t bit = w & 1u;
+            w >>= 1;
+            k = (bit && k + 1u < L) ? k + 1u : 0u;
+            const Mul next{__ldg(mrow + k)};     // for the next bin: off the dependent chain
+            core::fast_encode_arith(st, bit, mul, ev, ec);
+            worst = ec > worst ? ec : worst;
+            mul = next;
         }
-        const uint32_t bit = w & 1u;
-        w >>= 1;
-        k = (bit && k + 1u < L) ? k + 1u : 0u;
-        const Mul next{__ldg(mrow + k)};         // off the dependent chain of the step
-        core::fast_encode_bin(st, bac, bit, mul);
-        mul = next;
     }
+    bac.put(ev, ec < 32u ? ec : 0u);
+    return worst;
+}
+
+// The lean loop: rows with an invalid probability (errors in the reference's order) and streams in which one
+// bin released more than 31 bits.
+__device__ __noinline__ uint32_t encode_bins_lean(const double* __restrict__ prow, const uint32_t* __restrict__ uw,
+                                                  uint32_t nb, uint32_t L, uint8_t* slot, uint32_t cap_bits,
+                                                  uint32_t* nbits_out)
+{
+    core::BacState st = {0u, core::kRangeMax, 0u};
+    core::BitSink bac;
+    bac.init(slot, cap_bits);
+    uint32_t e = 0, k = 0;
+    for (uint32_t g = 0; g < nb && !e; g++) {
+        const uint32_t bit = (__ldg(uw + (g >> 5)) >> (g & 31u)) & 1u;
+        e = core::lean_encode_bin(st, bac, bit, __ldg(prow + k));
+        k = (bit && k + 1u < L) ? k + 1u : 0u;
+    }
+    if (!e) e = core::bac_finish(st, bac);
+    bac.flush();
+    *nbits_out = bac.nbits;
+    return e;
 }
 
 __global__ void __launch_bounds__(64)
@@ -341,33 +371,30 @@ encode_streams3_kernel(const uint32_t* __restrict__ nbins, const uint32_t* __res
     const uint32_t nb = nbins[s];
     uint8_t* slot = bac_slots + (size_t)s * slot_bytes;
     const uint32_t flags = row_flags ? row_flags[row] : (row_is_valid(prow, L) ? 1u : 0u);
-    core::BacState st = {0u, core::kRangeMax, 0u};
-    if (!(flags & 1u)) {
-        // a probability outside (0, 1): the lean loop reports errors in the reference's order
-        core::BitSink bac;
+    uint32_t nbits = 0, e = 0;
+    bool lean = !(flags & 1u);
+    if (!lean) {
+        core::BacState st = {0u, core::kRangeMax, 0u};
+        core::FastSink bac;
         bac.init(slot, cap_bits);
-        uint32_t e = 0, k = 0;
-        for (uint32_t g = 0; g < nb && !e; g++) {
-            const uint32_t bit = (__ldg(uw + (g >> 5)) >> (g & 31u)) & 1u;
-            e = core::lean_encode_bin(st, bac, bit, __ldg(prow + k));
-            k = (bit && k + 1u < L) ? k + 1u : 0u;
-        }
-        if (!e) e = core::bac_finish(st, bac);
+        const uint32_t worst = (flags & 2u)
+            ? encode_bins_fast<core::MulFixed48>(qtable + (size_t)row * L, uw, nb, L, st, bac)
+            : encode_bins_fast<core::MulFp64>(prow, uw, nb, L, st, bac);
+        core::fast_finish(st, bac);
         bac.flush();
-        bac_bits[s] = bac.nbits;
-        err[s] = e;
-        return;
+        nbits = bac.pos();
+        e = nbits > cap_bits ? core::kErrCapacity : 0u;
+        lean = worst > 31u;
     }
-    core::FastSink bac;
-    bac.init(slot, cap_bits);
-    if (flags & 2u) encode_bins_fast<core::MulFixed48>(qtable + (size_t)row * L, uw, nb, L, st, bac);
-    else encode_bins_fast<core::MulFp64>(prow, uw, nb, L, st, bac);
-    core::fast_finish(st, bac);
-    bac.flush();
-    bac_bits[s] = bac.pos;
-    err[s] = bac.pos > cap_bits ? core::kErrCapacity : 0u;
+    if (lean) e = encode_bins_lean(prow, uw, nb, L, slot, cap_bits, &nbits);
+    bac_bits[s] = nbits;
+    err[s] = e;
 }
 
+__device__ uint32_t g_empty_word = 0;   // stands in for a stream of zero bits
+
+// Fast prefix decoder of one stream: an unchecked single-basic-block loop while at least 32 bits of the stream
+// remain, then the checked step for the end of the stream.
 template <typename Mul, typename T>
 __device__ __forceinline__ void decode_prefixes_fast(const T* __restrict__ mrow, uint32_t L, uint32_t size,
                                                      core::FastSource& bac, int16_t* __restrict__ dst)
@@ -377,15 +404,28 @@ __device__ __forceinline__ void decode_prefixes_fast(const T* __restrict__ mrow,
     uint32_t i = 0, a = 0, k = 0;
     const Mul m0{__ldg(mrow)};
     Mul mul = m0;
-    while (i < size) {
+    int16_t* dptr = dst;
+    #pragma unroll 1
+    while (i < size && bac.left >= 32u) {
         // the next multiplier is entry 0 (symbol finished) or entry k + 1: fetch the latter before the bit is known
         const Mul up{__ldg(mrow + (k + 1u < L ? k + 1u : k))};
-        const uint32_t bit = core::fast_decode_bin(st, bac, mul);
+        const uint32_t bit = core::fast_decode_bin<false>(st, bac, mul);
+        a += bit;
+        const bool done = !bit || k == L - 1u;
+        if (done) *dptr = (int16_t)a;            // one predicated store; the pointer only advances
+        dptr += done ? 1 : 0;
+        i += done ? 1u : 0u;
+        a = done ? 0u : a;
+        k = done ? 0u : k + 1u;
+        mul = done ? m0 : up;
+    }
+    while (i < size) {
+        const uint32_t bit = core::fast_decode_bin<true>(st, bac, mul);
         a += bit;
         const bool done = !bit || k == L - 1u;
         if (done) { dst[i] = (int16_t)a; i++; a = 0; }
         k = done ? 0u : k + 1u;
-        mul = done ? m0 : up;
+        mul = Mul{__ldg(mrow + k)};
     }
 }
 
@@ -427,8 +467,16 @@ decode_streams3_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t s
             k = done ? 0u : k + 1u;
         }
     } else {
+        // The stream is read one word every few bins, each lane from its own cache lines: bring the lines into L1
+        // now so that no refill of the window waits for L2 / HBM in the middle of the dependent chain.
+        {
+            const uint8_t* sp = bac_base + bac_off[s];
+            const uint32_t nbytes = (bac_bits[s] + 7u) >> 3;
+            for (uint32_t o = 0; o < nbytes && o < 64u * 128u; o += 128u)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + o));
+        }
         core::FastSource bac;
-        bac.init(bac_base + bac_off[s], bac_bits[s]);
+        bac.init(bac_base + bac_off[s], bac_bits[s], &g_empty_word);
         if (flags & 2u) decode_prefixes_fast<core::MulFixed48>(qtable + (size_t)row * L, L, size, bac, dst);
         else decode_prefixes_fast<core::MulFp64>(prow, L, size, bac, dst);
     }

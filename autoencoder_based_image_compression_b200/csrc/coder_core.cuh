@@ -566,45 +566,50 @@ EAE_HD uint32_t fast_rescale(uint32_t& low, uint32_t& high, uint32_t low1, uint3
 }
 
 struct FastSink {
-    uint64_t acc;          // collected bits, first one at bit 63
-    uint32_t fill;         // number of collected bits, < 32 between calls
-    uint32_t pos;          // bits emitted so far
-    uint32_t widx;         // words stored so far
+    uint32_t cur;          // the word being filled, first bit at bit 31
+    uint32_t fill;         // bits in cur, < 32 between calls
+    uint32_t widx;         // whole words stored so far
     uint32_t spare;        // index of the word that absorbs stores past the capacity
     uint32_t* words;
 
     EAE_HD void init(uint8_t* slot, uint32_t cap_bits)
     {
         words = reinterpret_cast<uint32_t*>(slot);
-        acc = 0; fill = 0; pos = 0; widx = 0;
+        cur = 0; fill = 0; widx = 0;
         spare = (cap_bits + 31u) >> 5;      // the slot is at least 16 bytes longer than the capacity
     }
-    // Appends the c (0..32) low bits of v, most significant first.
+    EAE_HD uint32_t pos() const { return widx * 32u + fill; }
+    // Appends the c (0..31) low bits of v (v < 2^c), most significant first. No branch: the store of a
+    // completed word is the only conditional instruction.
     EAE_HD void put(uint32_t v, uint32_t c)
     {
-        acc |= (uint64_t)v << ((64u - fill - c) & 63u);   // fill + c <= 63; v = 0 when c = 0
+        const uint32_t top = shl_sat(v, 32u - c);
+        cur |= top >> fill;
+        const uint32_t spill = shl_sat(top, 32u - fill);
         fill += c;
-        pos += c;
-        if (fill >= 32u) {
-            words[widx < spare ? widx : spare] = brev32((uint32_t)(acc >> 32));
-            widx++;
-            acc <<= 32;
-            fill -= 32u;
-        }
+        const bool full = fill >= 32u;
+        if (full) words[widx < spare ? widx : spare] = brev32(cur);
+        widx += full ? 1u : 0u;
+        cur = full ? spill : cur;
+        fill -= full ? 32u : 0u;
     }
     EAE_HD void put_run(uint32_t bit, uint32_t repeat)
     {
         while (repeat) {
-            const uint32_t c = repeat < 32u ? repeat : 32u;
-            put(bit ? (c == 32u ? 0xFFFFFFFFu : ((1u << c) - 1u)) : 0u, c);
+            const uint32_t c = repeat < 31u ? repeat : 31u;
+            put(bit ? ((1u << c) - 1u) : 0u, c);
             repeat -= c;
         }
     }
-    EAE_HD void flush() { if (fill) words[widx < spare ? widx : spare] = brev32((uint32_t)(acc >> 32)); }
+    EAE_HD void flush() { if (fill) words[widx < spare ? widx : spare] = brev32(cur); }
 };
 
+// Arithmetic of one encoder bin. The bits it releases are returned as the `ec`-bit number `ev` (most
+// significant bit first) for FastSink::put, which the kernels call one iteration later so that the two
+// dependent chains overlap. ec can exceed 31 only after more than 15 consecutive E3 steps; callers then
+// redo the stream with the lean formulation.
 template <typename Mul>
-EAE_HD void fast_encode_bin(BacState& s, FastSink& out, uint32_t bit, const Mul& mul)
+EAE_HD void fast_encode_arith(BacState& s, uint32_t bit, const Mul& mul, uint32_t& ev, uint32_t& ec)
 {
     const uint32_t mid = s.low + mul(s.high - s.low);
     const uint32_t low1 = bit ? mid + 1u : s.low;
@@ -613,16 +618,9 @@ EAE_HD void fast_encode_bin(BacState& s, FastSink& out, uint32_t bit, const Mul&
     const uint32_t n = fast_rescale(s.low, s.high, low1, high1, k);
     const uint32_t q = n ? s.pending : 0u;         // follow bits leave with the first renormalisation bit
     s.pending = (n ? 0u : s.pending) + k;
-    const uint32_t e = low1 >> (16u - n);           // top n bits of low, MSB first
-    if (n + q <= 32u) {
-        const uint32_t follow = (uint32_t)((((1ull << q) - 1ull) << n) >> 1);
-        out.put(e + follow, n + q);
-    } else {
-        const uint32_t first = e >> (n - 1u);
-        out.put(first, 1u);
-        out.put_run(first ^ 1u, q);
-        out.put(e & ((1u << (n - 1u)) - 1u), n - 1u);
-    }
+    // n bits of low (MSB first) + q follow bits = (0 then q ones, from the bit after the first) + carry
+    ec = n + q;
+    ev = (low1 >> (16u - n)) + shr_sat(shl_sat(shl_sat(1u, q) - 1u, n), 1u);
 }
 
 // stop_encoding (BinaryArithmeticCoder.cpp:61-102) on the fast sink.
@@ -634,41 +632,40 @@ EAE_HD void fast_finish(BacState& s, FastSink& out)
 }
 
 // MSB-first window over an LSB-first packed stream at any byte alignment. `left` counts the real bits not yet
-// consumed; the window may hold bytes that follow the stream, which are never used (take() needs s <= left).
+// consumed; the window may also hold bytes that follow the stream, which are never used: take() needs
+// s <= left, take_padded() implements the reference's behaviour at the end of the stream. Word fetches are
+// clamped to the aligned span that contains the stream.
 struct FastSource {
     uint64_t win;          // next bit at bit 63
-    uint32_t have;         // bits in win
+    uint32_t have;         // bits in win, > 32 between calls
     uint32_t left;
     uint32_t next;         // prefetched word
-    uint32_t widx, nwords;
+    uint32_t widx, last;   // next word to fetch, index of the last word of the span
     const uint32_t* words;
 
-    EAE_HD uint32_t fetch()
-    {
-        const uint32_t w = widx < nwords ? load_ro(words + widx) : 0u;
-        widx++;
-        return w;
-    }
-    EAE_HD void init(const uint8_t* p, uint32_t bits)
+    // `empty` is any readable word; it stands in for a stream of zero bits.
+    EAE_HD void init(const uint8_t* p, uint32_t bits, const uint32_t* empty)
     {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        const uint32_t skip = (uint32_t)(a & 3u) * 8u;
-        words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        nwords = bits ? (skip + bits + 31u) >> 5 : 0u;
-        widx = 0; left = bits;
-        const uint32_t w0 = fetch();
-        win = (uint64_t)brev32(w0 >> skip) << 32;
+        const uint32_t skip = bits ? (uint32_t)(a & 3u) * 8u : 0u;
+        words = bits ? reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3) : empty;
+        last = bits ? ((skip + bits + 31u) >> 5) - 1u : 0u;
+        left = bits;
+        win = (uint64_t)brev32(load_ro(words) >> skip) << 32;
         have = 32u - skip;
-        next = fetch();
+        widx = 1;
+        next = load_ro(words + (widx < last ? widx : last));
+        widx++;
         refill();
     }
     EAE_HD void refill()
     {
-        if (have <= 32u) {
-            win |= (uint64_t)brev32(next) << (32u - have);
-            have += 32u;
-            next = fetch();
-        }
+        const bool need = have <= 32u;
+        const uint64_t add = (uint64_t)brev32(next) << ((32u - have) & 63u);
+        win |= need ? add : 0ull;
+        have += need ? 32u : 0u;
+        if (need) next = load_ro(words + (widx < last ? widx : last));
+        widx += need ? 1u : 0u;
     }
     // Next s (0..32) bits as a number, first bit most significant. Needs s <= left.
     EAE_HD uint32_t take(uint32_t s)
@@ -680,11 +677,11 @@ struct FastSource {
         refill();
         return v;
     }
-    // The reference's behaviour at the end of the stream (BinaryArithmeticCoder.cpp:275-315): the bits that
-    // are there, then the last of them (or 0) repeated.
+    // The reference's behaviour at the end of the stream (BinaryArithmeticCoder.cpp:104-122, 275-315): the
+    // bits that are there, then the last of them (or 0) repeated.
     EAE_HD uint32_t take_padded(uint32_t s)
     {
-        const uint32_t r = left;
+        const uint32_t r = left < s ? left : s;
         uint32_t v = 0u, in = 0u;
         if (r) { v = take(r); in = v & 1u; }
         for (uint32_t j = r; j < s; j++) v = (v << 1) | in;
@@ -695,10 +692,12 @@ struct FastSource {
 EAE_HD void fast_decode_start(DecState& s, FastSource& bac)
 {
     s.low = 0u; s.high = kRangeMax;
-    s.code = bac.left >= 16u ? bac.take(16u) : bac.take_padded(16u);
+    s.code = bac.take_padded(16u);
 }
 
-template <typename Mul>
+// One decoder bin. kChecked = false is the steady state (the caller guarantees left >= 30, so the n + k new
+// bits are there); kChecked = true also handles the end of the stream.
+template <bool kChecked, typename Mul>
 EAE_HD uint32_t fast_decode_bin(DecState& s, FastSource& bac, const Mul& mul)
 {
     const uint32_t mid = s.low + mul(s.high - s.low);
@@ -708,7 +707,7 @@ EAE_HD uint32_t fast_decode_bin(DecState& s, FastSource& bac, const Mul& mul)
     uint32_t k;
     const uint32_t n = fast_rescale(s.low, s.high, low1, high1, k);
     const uint32_t sh = n + k;
-    const uint32_t fresh = bac.left >= sh ? bac.take(sh) : bac.take_padded(sh);
+    const uint32_t fresh = kChecked ? bac.take_padded(sh) : bac.take(sh);
     s.code = (((s.code << sh) | fresh) & kRangeMax) ^ (k ? kMsb : 0u);
     return bit;
 }

@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--cpu-sample', type=int, default=0, help='images in the CPU sample (0 = one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--coder-lanes', type=int, default=4,
+    ap.add_argument('--coder-lanes', type=int, default=1,
                     help='GPU threads per coded stream (0 = one warp per stream: lowest latency)')
     ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '8')),
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')

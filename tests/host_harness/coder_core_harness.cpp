@@ -203,16 +203,21 @@ static int fixed48_matches(double p)
     return 1;
 }
 
+// Returns the largest number of bits one bin released (the fast sink takes at most 31 at a time).
 template <typename Mul>
 static uint32_t encode3_loop(const uint32_t* unary, uint32_t nbins, const Mul* muls, uint32_t L, BacState& st, FastSink& bac)
 {
-    uint32_t k = 0;
+    uint32_t k = 0, ev = 0, ec = 0, worst = 0;
     for (uint32_t g = 0; g < nbins; g++) {
+        bac.put(ev, ec);      // the previous bin's bits, as in the kernel's rotated loop
         const uint32_t bit = (unary[g >> 5] >> (g & 31)) & 1u;
-        fast_encode_bin(st, bac, bit, muls[k]);
+        fast_encode_arith(st, bit, muls[k], ev, ec);
+        if (ec > worst) worst = ec;
+        if (ec > 31u) return worst;
         k = (bit && k + 1u < L) ? k + 1u : 0u;
     }
-    return 0;
+    bac.put(ev, ec);
+    return worst;
 }
 
 // mode 0: FP64 multiplier, mode 1: fixed-point multiplier (when the table validates, as in the product).
@@ -248,25 +253,32 @@ extern "C" int harness_encode3(uint32_t size, const int16_t* in, uint32_t L, con
     bool fixed = mode == 1;
     for (uint32_t j = 0; j < L && fixed; j++) fixed = fixed48_matches(probs[j]);
     BacState st = {0u, kRangeMax, 0u};
+    uint32_t worst;
     if (fixed) {
         MulFixed48* m = (MulFixed48*)malloc(sizeof(MulFixed48) * L);
         for (uint32_t j = 0; j < L; j++) m[j].q = fixed48_of(probs[j]);
-        encode3_loop(unary, nbins, m, L, st, bac);
+        worst = encode3_loop(unary, nbins, m, L, st, bac);
         free(m);
     } else {
         MulFp64* m = (MulFp64*)malloc(sizeof(MulFp64) * L);
         for (uint32_t j = 0; j < L; j++) m[j].p = probs[j];
-        encode3_loop(unary, nbins, m, L, st, bac);
+        worst = encode3_loop(unary, nbins, m, L, st, bac);
         free(m);
+    }
+    if (worst > 31u) {     // more than 31 bits from one bin: the kernels redo the stream with the lean loop
+        free(a);
+        free(b);
+        free(unary);
+        return harness_encode2(size, in, L, probs, cap_bits, bac_out, bac_bits, byp_out, byp_bits);
     }
     fast_finish(st, bac);
     bac.flush();
     byp.flush();
-    const uint32_t e = bac.pos > cap_bits ? kErrCapacity : 0u;
-    *bac_bits = bac.pos;
+    const uint32_t e = bac.pos() > cap_bits ? kErrCapacity : 0u;
+    *bac_bits = bac.pos();
     *byp_bits = byp.nbits;
     if (!e) {
-        memcpy(bac_out, a, (bac.pos + 7) / 8);
+        memcpy(bac_out, a, (bac.pos() + 7) / 8);
         memcpy(byp_out, b, (byp.nbits + 7) / 8);
     }
     free(a);
@@ -291,7 +303,8 @@ extern "C" int harness_decode3(uint32_t size, int16_t* out, uint32_t L, const do
     memcpy(b + misalign, byp_in, nr);
     FastSource bac;
     BitSource byp;
-    bac.init(a + misalign, bac_bits);
+    static const uint32_t empty_word = 0;
+    bac.init(a + misalign, bac_bits, &empty_word);
     byp.init(b + misalign, byp_bits);
     bool fixed = mode == 1;
     for (uint32_t j = 0; j < L && fixed; j++) fixed = fixed48_matches(probs[j]);
@@ -300,8 +313,14 @@ extern "C" int harness_decode3(uint32_t size, int16_t* out, uint32_t L, const do
     uint32_t e = 0, i = 0, mag = 0, k = 0;
     while (i < size) {
         uint32_t bit;
-        if (fixed) bit = fast_decode_bin(st, bac, MulFixed48{fixed48_of(probs[k])});
-        else bit = fast_decode_bin(st, bac, MulFp64{probs[k]});
+        const bool steady = bac.left >= 32u;     // the kernel's unchecked loop runs while this holds
+        if (fixed) {
+            const MulFixed48 m{fixed48_of(probs[k])};
+            bit = steady ? fast_decode_bin<false>(st, bac, m) : fast_decode_bin<true>(st, bac, m);
+        } else {
+            const MulFp64 m{probs[k]};
+            bit = steady ? fast_decode_bin<false>(st, bac, m) : fast_decode_bin<true>(st, bac, m);
+        }
         mag += bit;
         if (!bit || k == L - 1u) { out[i++] = (int16_t)mag; mag = 0; k = 0; } else k++;
     }
