@@ -20,6 +20,7 @@ struct eae_codec {
     int umma_mask = 0xF;   // which layer kinds run on tensor cores (debug: env EAE_UMMA_LAYERS)
     uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
+    int no_direct_conv1 = 0;   // debug: env EAE_NO_DIRECT_CONV1=1 keeps the im2col pass in front of layer 1
     cudaStream_t own_stream = nullptr;
 
     // ---- weights (device) ----
@@ -291,12 +292,16 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     float* A = c->bufA.as<float>();
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
-    // layer 1: conv k9 s4 (1 -> 128) as im2col + one 96-deep contraction, GDN; output parity-split for the
-    // stride-2 layer that follows
-    { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
+    // layer 1: conv k9 s4 (1 -> 128) as one 96-deep contraction (81 taps used) + GDN; output parity-split for the
+    // stride-2 layer that follows. On the tensor path (kernel version 3) the patches are gathered from the uint8
+    // image inside the kernel; otherwise an im2col pass writes them out first.
     {
+        const bool direct = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() == 3 &&
+                            !c->no_direct_conv1;
+        if (!direct) { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
         p.out_split = 1;
+        if (direct) { p.img_u8 = img_dev; p.img_H = (int)h; p.img_W = (int)w; }
         EAE_TRY(run_layer(c, &p, 1, kLayerThin, umma_weights(c, 0, 1), 0, false, p.M, st));
     }
     // layer 2 (output parity-split again), layer 3 (natural NHWC: it is the latent the API returns)
@@ -622,6 +627,7 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     }
     if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
     if (const char* env = getenv("EAE_NO_FUSE")) c->no_fuse = atoi(env);
+    if (const char* env = getenv("EAE_NO_DIRECT_CONV1")) c->no_direct_conv1 = atoi(env);
     *out = c.release();
     return 0;
 }

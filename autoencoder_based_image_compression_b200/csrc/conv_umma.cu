@@ -361,6 +361,7 @@ struct UmmaParams2 {
     int n_tiles;             // real tiles; the grid is rounded up to a multiple of `cluster`
     int tile_w_log2;
     int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
+    int conv1;               // version 3: A rows are the 9x9 patches (k9 s4) of a uint8 image tile staged by TMA
     int debug;               // timing experiments (env EAE_UMMA_DEBUG): 1 no conversion, 2 no MMA, 4 no B loads, 8 no A loads
     uint32_t* error_flag;
     UmmaTap taps[kMaxTaps];
@@ -683,9 +684,31 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 //  smem: 3 stages x { A0 16K | A1 16K | B_hi 16K | B_lo 16K }.
 constexpr int kStages3 = 3;
 constexpr int kStageBytes3 = 4 * kTileBytes;
-constexpr int kSmemBytes3 = kStages3 * kStageBytes3 + 1024 + 256;
+// uint8 image region of 16 x 16 positions of the k9 s4 convolution: rows 4 a0 - 2 .. + 68, columns from 4 b0 - 16
+// (TMA needs a 16-byte aligned start in the innermost dimension; the patches start kImgPadX = 14 bytes in).
+constexpr int kImgBoxW = 96, kImgBoxH = 69, kImgPadX = 14;
+constexpr int kImgBytes = ((kImgBoxW * kImgBoxH + 127) / 128) * 128;
+constexpr int kSmemBytes3 = kStages3 * kStageBytes3 + kImgBytes + 1024 + 256;
 constexpr int kUmmaThreads3 = 320;
 constexpr uint32_t kCol3Acc0 = 0, kCol3Acc1 = 128, kCol3Slots = 256, kCol3Nrm0 = 256, kCol3Nrm1 = 384;
+
+// 32 consecutive im2col entries (k = ky * 9 + kx, chunk kChunk of three) of one 9x9 uint8 patch as fp32 bit
+// patterns: a byte b becomes 0x4B0000bb = 2^23 + b, minus 2^23 (exact).
+template <int kChunk>
+__device__ __forceinline__ void patch_chunk(const uint8_t* __restrict__ patch, uint32_t* r)
+{
+    #pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const int k = kChunk * 32 + i;
+        if (k < 81) {
+            const int ky = k / 9, kx = k % 9 + (kImgPadX & 3);     // `patch` is the 4-byte aligned address before the patch
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(patch + ky * kImgBoxW + (kx & ~3));
+            r[i] = __float_as_uint(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + (kx & 3))) - 8388608.f);
+        } else {
+            r[i] = 0u;
+        }
+    }
+}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
 {
@@ -695,17 +718,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
 __global__ void __launch_bounds__(kUmmaThreads3, 1)
 gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
-                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams2 p)
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ CUtensorMap map_img,
+                  const __grid_constant__ UmmaParams2 p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages3 * kStageBytes3);
+    uint8_t* img_tile = smem + kStages3 * kStageBytes3;      // conv1: [69 rows][80] uint8, rows/cols outside the image are 0
+    uint64_t* bars = reinterpret_cast<uint64_t*>(img_tile + kImgBytes);
     uint64_t* full = bars;
     uint64_t* split = bars + kStages3;
     uint64_t* empty = bars + 2 * kStages3;
     uint64_t* acc_full = bars + 3 * kStages3;
     uint64_t* nrm_full = bars + 3 * kStages3 + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages3 + 2);
+    uint64_t* img_full = bars + 3 * kStages3 + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages3 + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile = tile_w x (2 * tile_h) positions: half h covers rows [a0 + h * tile_h, +tile_h)
@@ -722,6 +748,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
+        mbar_init(img_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -736,6 +763,8 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
     const int n_main = p.n_taps * p.kchunks;
     const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
+    // conv1: the A operand is an exact small integer (a pixel), so it has no low part
+    const bool a_has_lo = p.exact_main && !p.conv1;
     const int n_total = n_main + n_gdn;
 
     if (warp == 0) {
@@ -745,7 +774,15 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const int s = it % kStages3;
                 if (!mbar_wait(&empty[s], ((it / kStages3) & 1) ^ 1, p.error_flag, 0)) break;
                 uint8_t* st = smem + s * kStageBytes3;
-                if (it < n_main) {
+                if (it < n_main && p.conv1) {
+                    if (it == 0) {      // the uint8 image region of this tile (SAME padding = out-of-bounds zero fill)
+                        mbar_expect_tx(img_full, kImgBoxW * kImgBoxH);
+                        tma_load_3d(img_tile, &map_img, img_full, 4 * b0 - 2 - kImgPadX, 4 * a0 - 2, img);
+                    }
+                    mbar_expect_tx(&full[s], (p.exact_main ? 2 : 1) * kTileBytes);
+                    tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full[s], it * kChunkK, 0, 0);
+                    if (p.exact_main) tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full[s], it * kChunkK, 0, 0);
+                } else if (it < n_main) {
                     const int t = it / p.kchunks, kc = it - t * p.kchunks;
                     const UmmaTap tap = p.taps[t];
                     mbar_expect_tx(&full[s], (p.exact_main ? 4 : 3) * kTileBytes);
@@ -780,10 +817,8 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         for (int k = 0; k < kChunkK / 8; k++) {
                             const uint64_t b_hi = make_desc(st + 2 * kTileBytes + k * 32);
                             umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
-                            if (p.exact_main) {
-                                umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
-                                umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + 3 * kTileBytes + k * 32), 1u);
-                            }
+                            if (a_has_lo) umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
+                            if (p.exact_main) umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + 3 * kTileBytes + k * 32), 1u);
                         }
                     }
                 } else {
@@ -825,6 +860,26 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t slot = lane_base + kCol3Slots + 128u * (uint32_t)(it & 1);
+                if (p.conv1) {
+                    // A rows straight from the pixels: row (a, b) of half h is the 9x9 patch whose top-left pixel is
+                    // tile byte (4 (8 h + a), 4 b); chunk `it` covers k = ky * 9 + kx in [32 it, 32 it + 32), k >= 81 is 0.
+                    if (it == 0 || it == 1) {
+                        ok = mbar_wait(img_full, 0, p.error_flag, 6);
+                        if (!ok) break;
+                    }
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint8_t* patch = img_tile + (4 * (8 * h + (row >> 4))) * kImgBoxW + (kImgPadX & ~3) + 4 * (row & 15);
+                        if (it == 0) patch_chunk<0>(patch, r);
+                        else if (it == 1) patch_chunk<1>(patch, r);
+                        else patch_chunk<2>(patch, r);
+                        tmem_st32(slot + 64u * (uint32_t)h, r);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&split[s]);
+                    continue;
+                }
                 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint8_t* rowp = st + h * kTileBytes + row * 128;
@@ -996,6 +1051,22 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
     return 0;
 }
 
+// uint8 image [n, H, W] -> boxes of kImgBoxW x kImgBoxH pixels of one image, no swizzle, zero fill outside.
+int make_map_u8(CUtensorMap* map, const void* base, uint64_t W, uint64_t H, uint64_t n)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EAE_ERR_CUDA; }
+    const cuuint64_t gdim[3] = {W, H, n};
+    const cuuint64_t gstride[2] = {W, W * H};
+    const cuuint32_t bdim[3] = {(cuuint32_t)kImgBoxW, (cuuint32_t)kImgBoxH, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, bdim, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (uint8 image) failed with CUresult %d", (int)r); return EAE_ERR_CUDA; }
+    return 0;
+}
+
 uint32_t* g_error_flag = nullptr;   // device word, per process (one device per process in practice)
 
 }  // namespace
@@ -1085,13 +1156,22 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         u.w_tap = (int)(plan.taps[t].w_off / ((uint32_t)plan.Cin * kCout));
     }
     CUtensorMap map_a, map_b_hi, map_b_lo;
-    const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
-    const uint32_t abox[5] = {kChunkK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
-    EAE_TRY(make_map(&map_a, plan.in, 5, adims, abox));
     const uint64_t bdims[3] = {(uint64_t)plan.Cin, kCout, (uint64_t)w.n_taps};
     const uint32_t bbox[3] = {kChunkK, kCout, 1};
     EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
+    if (plan.img_u8) {
+        if (umma_version() != 3 || plan.n_taps != 1 || plan.Cin != 96 || plan.Hg * 4 != plan.img_H ||
+            plan.Wg * 4 != plan.img_W || plan.img_W % 16 != 0) {
+            set_error("gemm_umma: the fused k9 s4 convolution needs kernel version 3 and a [n, 4 Hg, 4 Wg] image");
+            return EAE_ERR_ARGUMENT;
+        }
+        map_a = map_b_hi;      // not read
+    } else {
+        const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
+        const uint32_t abox[5] = {kChunkK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
+        EAE_TRY(make_map(&map_a, plan.in, 5, adims, abox));
+    }
     const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
     if (umma_version() == 3) {
         UmmaParams2 q;
@@ -1114,7 +1194,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         memcpy(q.taps, p.taps, sizeof q.taps);
         const uint32_t grid3 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
         q.n_tiles = (int)grid3;
-        CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo;
+        CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo, map_img = map_b_hi;
         if (plan.fuse) {
             if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias) {
                 set_error("gemm_umma: fused GDN needs gamma hi/lo, beta and a bias-mode contraction");
@@ -1124,12 +1204,16 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
             EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
         }
+        if (plan.img_u8) {
+            q.conv1 = 1;
+            EAE_TRY(make_map_u8(&map_img, plan.img_u8, (uint64_t)plan.img_W, (uint64_t)plan.img_H, n_img));
+        }
         static bool attr3_done = false;
         if (!attr3_done) {
             EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
             attr3_done = true;
         }
-        gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+        gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
         EAE_LAUNCH_OK();
         return 0;
     }
