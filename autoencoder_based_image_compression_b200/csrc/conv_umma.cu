@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 #include "conv_plan.cuh"
@@ -363,6 +364,7 @@ struct UmmaParams2 {
     int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
     int conv1;               // version 3: A rows are the 9x9 patches (k9 s4) of a uint8 image tile staged by TMA
     int debug;               // timing experiments (env EAE_UMMA_DEBUG): 1 no conversion, 2 no MMA, 4 no B loads, 8 no A loads
+    long long* times;        // version 3, env EAE_UMMA_TIMING=1: [grid][8] clock64 stamps of the phases of each CTA
     uint32_t* error_flag;
     UmmaTap taps[kMaxTaps];
 };
@@ -412,6 +414,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r)
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
@@ -734,6 +742,8 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages3 + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
+    if (stamp && threadIdx.x == 64) stamp[0] = clock64();
     // tile = tile_w x (2 * tile_h) positions: half h covers rows [a0 + h * tile_h, +tile_h)
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int img = blockIdx.x / tiles_per_img;
@@ -760,6 +770,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (stamp && threadIdx.x == 64) stamp[1] = clock64();
 
     const int n_main = p.n_taps * p.kchunks;
     const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
@@ -835,7 +846,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                 }
                 umma_commit(&empty[s]);
-                if (it == n_main - 1) umma_commit(acc_full);
+                if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
                 if (n_gdn && it == n_total - 1) umma_commit(nrm_full);
             }
         }
@@ -851,6 +862,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int s = it % kStages3;
             ok = mbar_wait(&full[s], (it / kStages3) & 1, p.error_flag, 2);
             if (!ok) break;
+            if (stamp && it == 0 && threadIdx.x == 64) stamp[2] = clock64();
             uint8_t* st = smem + s * kStageBytes3;
             if (it < n_main) {
                 // TMEM slot (it & 1) was last read by the MMAs of iteration it - 2
@@ -909,6 +921,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     ok = mbar_wait(acc_full, 0, p.error_flag, 3);
                     if (!ok) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (stamp && threadIdx.x == 64) stamp[4] = clock64();
                 }
                 const int g = it - n_main, h = g >> 2, c0 = (g & 3) * kChunkK;
                 tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
@@ -937,6 +950,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (stamp && threadIdx.x == 64) stamp[5] = clock64();
 
         // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (stage h of the ring,
         // four swizzled [128 x 32] sub-tiles) -> coalesced 512-byte rows.
@@ -946,8 +960,9 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             #pragma unroll 1
             for (int cc = 0; cc < 2; cc++) {
                 const int c0 = set * 64 + cc * 32;
-                tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                if (n_gdn) tmem_ld32(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
+                tmem_ld32_nowait(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                if (n_gdn) tmem_ld32_nowait(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
+                tmem_ld_wait();
                 uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
                 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -974,39 +989,57 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
         named_bar_sync(1, 256);     // both sets finished staging
-        const int wq = warp - 2;    // 0..7: rows wq, wq + 8, ... of each half
+        if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+        // Coalesced stores: warp wq writes rows wq, wq + 8, ... of each half, one 512-byte pixel per instruction;
+        // four rows are in flight at a time.
+        const int wq = warp - 2;
+        const bool fixup = !n_gdn && p.mode != kEpiBias;    // standalone GDN / IGDN
         #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const uint8_t* stage = smem + h * kStageBytes3;
             #pragma unroll 1
-            for (int rr = wq; rr < kTileM; rr += 8) {
-                const int a = a0 + h * p.half_da + (rr >> p.tile_w_log2), b = b0 + h * p.half_db + (rr & (p.tile_w - 1));
-                if (!(ok && a < p.Hg && b < p.Wg)) continue;
-                const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
-                size_t opix;
-                if (p.out_split)
-                    opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
-                else
-                    opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
-                float4 v = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 +
+            for (int j0 = 0; j0 < kTileM / 8; j0 += 4) {
+                float4 v[4];
+                float* dst[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int rr = wq + 8 * (j0 + j);
+                    const int a = a0 + h * p.half_da + (rr >> p.tile_w_log2), b = b0 + h * p.half_db + (rr & (p.tile_w - 1));
+                    const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
+                    size_t opix;
+                    if (p.out_split)
+                        opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
+                    else
+                        opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+                    dst[j] = (ok && a < p.Hg && b < p.Wg) ? p.out + opix * kCout + lane * 4 : nullptr;
+                    v[j] = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 +
                                                             (((lane & 7) ^ (rr & 7)) << 4));
-                if (!n_gdn && p.mode != kEpiBias) {
-                    // standalone GDN / IGDN: v holds norm (+ beta via bias); combine with the un-squared input
-                    const float4 x = *reinterpret_cast<const float4*>(p.xin + opix * kCout + lane * 4);
-                    if (p.mode == kEpiGdn) {
-                        v.x = __fdiv_rn(x.x, __fsqrt_rn(v.x)); v.y = __fdiv_rn(x.y, __fsqrt_rn(v.y));
-                        v.z = __fdiv_rn(x.z, __fsqrt_rn(v.z)); v.w = __fdiv_rn(x.w, __fsqrt_rn(v.w));
-                    } else {
-                        v.x = __fmul_rn(x.x, __fsqrt_rn(v.x)); v.y = __fmul_rn(x.y, __fsqrt_rn(v.y));
-                        v.z = __fmul_rn(x.z, __fsqrt_rn(v.z)); v.w = __fmul_rn(x.w, __fsqrt_rn(v.w));
+                }
+                if (fixup) {
+                    // v holds norm (+ beta via bias); combine with the un-squared input
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (!dst[j]) continue;
+                        const float4 x = *reinterpret_cast<const float4*>(p.xin + (dst[j] - p.out));
+                        if (p.mode == kEpiGdn) {
+                            v[j].x = __fdiv_rn(x.x, __fsqrt_rn(v[j].x)); v[j].y = __fdiv_rn(x.y, __fsqrt_rn(v[j].y));
+                            v[j].z = __fdiv_rn(x.z, __fsqrt_rn(v[j].z)); v[j].w = __fdiv_rn(x.w, __fsqrt_rn(v[j].w));
+                        } else {
+                            v[j].x = __fmul_rn(x.x, __fsqrt_rn(v[j].x)); v[j].y = __fmul_rn(x.y, __fsqrt_rn(v[j].y));
+                            v[j].z = __fmul_rn(x.z, __fsqrt_rn(v[j].z)); v[j].w = __fmul_rn(x.w, __fsqrt_rn(v[j].w));
+                        }
                     }
                 }
-                *reinterpret_cast<float4*>(p.out + opix * kCout + lane * 4) = v;
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (dst[j]) *reinterpret_cast<float4*>(dst[j]) = v[j];
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    // (a clock read right after a barrier gives the time this warp ISSUED the barrier, not its release)
+    if (stamp && threadIdx.x == 64) stamp[7] = clock64();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
     }
@@ -1212,6 +1245,34 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         if (!attr3_done) {
             EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
             attr3_done = true;
+        }
+        static int timing = -1;
+        if (timing < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing = e ? atoi(e) : 0; }
+        if (timing) {
+            // Debug: per-CTA phase stamps, averaged over the grid, printed to stderr (synchronises the stream).
+            long long* d_times = nullptr;
+            EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid3 * 8 * sizeof(long long)));
+            EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid3 * 8 * sizeof(long long), st));
+            q.times = d_times;
+            gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
+            EAE_LAUNCH_OK();
+            std::vector<long long> h((size_t)grid3 * 8);
+            EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            EAE_CUDA_OK(cudaStreamSynchronize(st));
+            cudaFree(d_times);
+            for (uint32_t b = 0; b < grid3; b += (grid3 / 3 ? grid3 / 3 : 1))
+                fprintf(stderr, "  cta %u raw: %lld | +%lld +%lld +%lld +%lld +%lld +%lld +%lld\n", b, h[(size_t)b * 8],
+                        h[(size_t)b * 8 + 1] - h[(size_t)b * 8], h[(size_t)b * 8 + 2] - h[(size_t)b * 8], h[(size_t)b * 8 + 3] - h[(size_t)b * 8],
+                        h[(size_t)b * 8 + 4] - h[(size_t)b * 8], h[(size_t)b * 8 + 5] - h[(size_t)b * 8], h[(size_t)b * 8 + 6] - h[(size_t)b * 8],
+                        h[(size_t)b * 8 + 7] - h[(size_t)b * 8]);
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t b = 0; b < grid3; b++)
+                for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 8 + j] - h[(size_t)b * 8]);
+            fprintf(stderr, "umma3 taps %d kchunks %d fuse %d conv1 %d grid %u: setup %.0f first_full %.0f main_issued %.0f acc_seen %.0f "
+                            "nrm_seen %.0f staged %.0f end %.0f (avg cycles from CTA start)\n",
+                    q.n_taps, q.kchunks, q.fuse, q.conv1, grid3, acc[1] / grid3, acc[2] / grid3, acc[3] / grid3, acc[4] / grid3,
+                    acc[5] / grid3, acc[6] / grid3, acc[7] / grid3);
+            return 0;
         }
         gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
         EAE_LAUNCH_OK();

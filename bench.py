@@ -406,16 +406,29 @@ def run_gpu_arm(args):
             bf16_peak = float(json.load(f)['bf16_tflops'])
         peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst)'
     achieved = gflop/gemm_ms if gemm_ms > 0 else 0.     # GFLOP / ms = TFLOP/s
+    # MMA work actually issued: tf32x3 = 3 MMAs per product (2 for layer 1, whose pixel operand is exact in TF32);
+    # GDN / IGDN always use the 3-way split; fp32 = CUDA cores (no MMAs).
+    passes = {'tf32': {'gemm_conv': 1., 'gemm_tconv': 1., 'gemm_gdn': 3., 'gemm_thin': 1.},
+              'tf32x3': {'gemm_conv': 3., 'gemm_tconv': 3., 'gemm_gdn': 3., 'gemm_thin': 2.5},
+              'fp32': {'gemm_conv': 0., 'gemm_tconv': 0., 'gemm_gdn': 0., 'gemm_thin': 0.}}[args.math]
+    executed = sum(GFLOP_PER_IMAGE[k]*passes[k] for k in GFLOP_PER_IMAGE)*scale*n*args.steps/gemm_ms if gemm_ms > 0 else 0.
+    # DRAM bytes per launch of this kernel from the committed ncu capture of this workload
+    # (profiles/r01_ncu_full_gemm_umma3_layers.md: 13 launches per step, 1805 MB per 24-image step).
+    traffic = 1804.9e6/13.*(n/24.)*scale if args.math != 'fp32' else None
     line['roofline'] = {
         'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
         'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',
-        'frac': achieved/(bf16_peak/2.) if bf16_peak else None, 'traffic': None,
+        'frac': achieved/(bf16_peak/2.) if bf16_peak else None, 'traffic': traffic,
         'peak_source': peak_src + ' / 2: tcgen05 kind::tf32 runs at half the bf16 rate; fp32 data, so the TF32 '
                                   'tensor peak is the bound the north star names',
         'measured_in': 'the serial pass of the same steps inside this run (CUDA events around every launch)',
         'algorithmic_gflop_per_step': gflop/args.steps, 'launches_per_step': gemm_launches/args.steps,
         'avg_launch_ms': gemm_ms/gemm_launches if gemm_launches else None,
         'share_of_step': gemm_ms/serial_ms if serial_ms else None,
+        'executed_mma_tflops': executed, 'frac_executed': executed/(bf16_peak/2.) if bf16_peak else None,
+        'note': 'achieved / frac count ALGORITHMIC flops (SURVEY 8d); the index-exact mode issues 3 TF32 MMAs per '
+                'product, so frac <= 1/3 by construction and frac_executed is the tensor-pipe view of the same time; '
+                'traffic = dram read + write bytes per launch from the ncu capture under profiles/',
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = run_cpu_arm(args, steps=1, warmup=1)

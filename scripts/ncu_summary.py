@@ -76,9 +76,10 @@ def main():
                 vals[m] = r[col[m]]
                 print('| {} (`{}`) | {} {} |'.format(label, m, r[col[m]], units[col[m]]))
         try:
-            rd = float(vals['dram__bytes_read.sum'].replace(',', ''))
-            wr = float(vals['dram__bytes_write.sum'].replace(',', ''))
-            print('| **DRAM traffic (read + write)** | {:.3f} {} |'.format(rd + wr, units[col['dram__bytes_read.sum']]))
+            scale = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1., 'Gbyte': 1e3}
+            rd = float(vals['dram__bytes_read.sum'].replace(',', ''))*scale[units[col['dram__bytes_read.sum']]]
+            wr = float(vals['dram__bytes_write.sum'].replace(',', ''))*scale[units[col['dram__bytes_write.sum']]]
+            print('| **DRAM traffic (read + write)** | {:.3f} Mbyte |'.format(rd + wr))
         except (KeyError, ValueError):
             pass
         try:
