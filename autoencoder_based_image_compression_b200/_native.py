@@ -101,6 +101,8 @@ PROTOTYPES = {
     'eae_cast_bt601_host': (c_int, [c_void_p, c_void_p, u64, c_void_p]),
     'eae_sum_squared_error_u8_host': (c_int, [c_void_p, c_void_p, u64, P(u64), c_void_p]),
     'eae_count_nb_deads_host': (c_int, [c_void_p, u32, u64, u32, c_void_p, c_void_p]),
+    'eae_latent_statistics_host': (c_int, [c_void_p, u64, u32, c_void_p, c_void_p, c_void_p, c_void_p, u32, P(u32),
+                                           c_void_p, c_void_p, u32, c_void_p, c_void_p]),
     'eae_codec_create': (c_int, [P(c_void_p), P(Weights), c_int, c_int]),
     'eae_codec_destroy': (c_int, [c_void_p]),
     'eae_codec_set_math': (c_int, [c_void_p, c_int]),

@@ -372,3 +372,175 @@ extern "C" int eae_rescale_compress_lossless_maps_host(const float* cq_hwc, uint
     }
     return 0;
 }
+
+// =================================================================================================
+// Latent statistics (kodak_tensorflow/lossless/stats.py): the counting part of save_statistics over a
+// calibration set of latents. The float64 epilogues (probabilities, divergences) stay on the host, in
+// numpy's order, in kodak_tensorflow/lossless/stats.py of this package.
+namespace eae {
+namespace {
+
+// Order-preserving map float -> uint32 (for atomicMin / atomicMax on floats of either sign).
+__device__ __forceinline__ uint32_t float_key(float x)
+{
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+inline float key_float(uint32_t k)
+{
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// Pass 1: per-map sum (float64), minimum and maximum. One thread owns one map of a slab of rows.
+__global__ void __launch_bounds__(256)
+stats_moments_kernel(const float* __restrict__ y, uint64_t n_rows, uint32_t C, double* __restrict__ sum,
+                     uint32_t* __restrict__ min_key, uint32_t* __restrict__ max_key, uint64_t rows_per_block)
+{
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_block;
+    const uint64_t r1 = r0 + rows_per_block < n_rows ? r0 + rows_per_block : n_rows;
+    for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = 0.;
+        float mn = INFINITY, mx = -INFINITY;
+        for (uint64_t r = r0; r < r1; r++) {
+            const float v = __ldg(y + r * C + c);
+            s += (double)v;
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+        if (r1 > r0) {
+            atomicAdd(&sum[c], s);
+            atomicMin(&min_key[c], float_key(mn));
+            atomicMax(&max_key[c], float_key(mx));
+        }
+    }
+}
+
+// Pass 2a: unit-interval histogram per map: bin floor(y - left[c]), the right edge belongs to the last
+// bin (numpy.histogram, stats.py:118-127 with size_interval 1).
+__global__ void __launch_bounds__(256)
+stats_unit_hist_kernel(const float* __restrict__ y, uint64_t n_elems, uint32_t C, const double* __restrict__ left,
+                       const uint32_t* __restrict__ nb_bins, unsigned long long* __restrict__ hist, uint32_t cap)
+{
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_elems;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(t % C);
+        const double d = floor((double)__ldg(y + t) - left[c]);
+        uint32_t b = d < 0. ? 0u : (uint32_t)d;
+        if (b >= nb_bins[c]) b = nb_bins[c] - 1u;
+        atomicAdd(&hist[(size_t)c * cap + b], 1ull);
+    }
+}
+
+// Pass 2b: counts of a = min(|rint((y - mean[c]) / delta[c])|, L) per map (L + 1 bins), privatised per CTA in
+// shared memory [L + 1][C].
+__global__ void __launch_bounds__(256)
+stats_abs_index_kernel(const float* __restrict__ y, uint64_t n_rows, uint32_t C, const float* __restrict__ mean,
+                       const float* __restrict__ delta, uint32_t L, unsigned long long* __restrict__ counts,
+                       uint64_t rows_per_block)
+{
+    extern __shared__ uint32_t sh_cnt[];
+    for (uint32_t i = threadIdx.x; i < (L + 1u) * C; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_block;
+    const uint64_t r1 = r0 + rows_per_block < n_rows ? r0 + rows_per_block : n_rows;
+    const uint64_t e1 = r1 * C;
+    for (uint64_t t = r0 * C + threadIdx.x; t < e1; t += blockDim.x) {
+        const uint32_t c = (uint32_t)(t % C);
+        // numpy float32 arithmetic of stats.py:42-44 / tools.py:927-929: (y - mean) / delta, round half to even
+        const float k = rintf(__fdiv_rn(__fsub_rn(__ldg(y + t), __ldg(mean + c)), __ldg(delta + c)));
+        const float a = fabsf(k);
+        const uint32_t bin = a < (float)L ? (uint32_t)a : L;
+        atomicAdd(&sh_cnt[bin * C + c], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (L + 1u) * C; i += blockDim.x) {
+        const uint32_t v = sh_cnt[i];
+        if (v) atomicAdd(&counts[(size_t)(i % C) * (L + 1u) + i / C], (unsigned long long)v);
+    }
+}
+
+}  // namespace
+}  // namespace eae
+
+extern "C" int eae_latent_statistics_host(const float* y, uint64_t n_rows, uint32_t nb_maps, double* sum_out,
+                                          float* min_out, float* max_out, uint64_t* unit_hist_out,
+                                          uint32_t unit_cap, uint32_t* needed_cap, const float* mean,
+                                          const float* delta, uint32_t L, uint64_t* abs_counts_out, void* stream)
+{
+    if (!y || !sum_out || !min_out || !max_out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (abs_counts_out && (!mean || !delta)) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (nb_maps == 0 || n_rows == 0) { set_error("empty latent array"); return EAE_ERR_ARGUMENT; }
+    if (abs_counts_out && (L == 0 || L > 255)) { set_error("truncated unary length %u not in [1, 255]", L); return L == 0 ? EAE_ERR_UNARY_LENGTH : EAE_ERR_ARGUMENT; }
+    if (abs_counts_out && n_rows > 0xFFFFFFFFull * 8) { set_error("too many rows"); return EAE_ERR_ARGUMENT; }
+    EAE_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n_elems = n_rows * nb_maps;
+    DevBuf dy, dsum, dmin, dmax;
+    EAE_TRY(dy.alloc(n_elems * 4));
+    EAE_TRY(dsum.alloc((size_t)nb_maps * 8));
+    EAE_TRY(dmin.alloc((size_t)nb_maps * 4));
+    EAE_TRY(dmax.alloc((size_t)nb_maps * 4));
+    EAE_CUDA_OK(cudaMemcpyAsync(dy.p, y, n_elems * 4, cudaMemcpyHostToDevice, st));
+    EAE_CUDA_OK(cudaMemsetAsync(dsum.p, 0, (size_t)nb_maps * 8, st));
+    EAE_CUDA_OK(cudaMemsetAsync(dmin.p, 0xFF, (size_t)nb_maps * 4, st));
+    EAE_CUDA_OK(cudaMemsetAsync(dmax.p, 0, (size_t)nb_maps * 4, st));
+    const uint32_t blocks = (uint32_t)(n_rows < 148ull * 8 ? n_rows : 148ull * 8);
+    const uint64_t rows_per_block = (n_rows + blocks - 1) / blocks;
+    stats_moments_kernel<<<blocks, 256, 0, st>>>(dy.as<float>(), n_rows, nb_maps, dsum.as<double>(), dmin.as<uint32_t>(),
+                                                 dmax.as<uint32_t>(), rows_per_block);
+    EAE_LAUNCH_OK();
+    std::unique_ptr<uint32_t[]> kmin(new uint32_t[nb_maps]), kmax(new uint32_t[nb_maps]);
+    EAE_CUDA_OK(cudaMemcpyAsync(sum_out, dsum.p, (size_t)nb_maps * 8, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(kmin.get(), dmin.p, (size_t)nb_maps * 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(kmax.get(), dmax.p, (size_t)nb_maps * 4, cudaMemcpyDeviceToHost, st));
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    uint32_t need = 1;
+    std::unique_ptr<double[]> left(new double[nb_maps]);
+    std::unique_ptr<uint32_t[]> nbins(new uint32_t[nb_maps]);
+    for (uint32_t c = 0; c < nb_maps; c++) {
+        min_out[c] = key_float(kmin[c]);
+        max_out[c] = key_float(kmax[c]);
+        left[c] = floor((double)min_out[c]);                       // stats.py:103-104
+        const double width = ceil((double)max_out[c]) - left[c];
+        nbins[c] = width >= 1. ? (width > 4e9 ? 0xFFFFFFFFu : (uint32_t)width) : 1u;
+        if (nbins[c] > need) need = nbins[c];
+    }
+    if (needed_cap) *needed_cap = need;
+    if (unit_hist_out) {
+        if (need > unit_cap) { set_error("unit histogram range %u exceeds unit_cap %u", need, unit_cap); return EAE_ERR_ARGUMENT; }
+        DevBuf dleft, dnb, dhist;
+        EAE_TRY(dleft.alloc((size_t)nb_maps * 8));
+        EAE_TRY(dnb.alloc((size_t)nb_maps * 4));
+        EAE_TRY(dhist.alloc((size_t)nb_maps * unit_cap * 8));
+        EAE_CUDA_OK(cudaMemcpyAsync(dleft.p, left.get(), (size_t)nb_maps * 8, cudaMemcpyHostToDevice, st));
+        EAE_CUDA_OK(cudaMemcpyAsync(dnb.p, nbins.get(), (size_t)nb_maps * 4, cudaMemcpyHostToDevice, st));
+        EAE_CUDA_OK(cudaMemsetAsync(dhist.p, 0, (size_t)nb_maps * unit_cap * 8, st));
+        stats_unit_hist_kernel<<<grid_for(n_elems, 4), kThreads, 0, st>>>(dy.as<float>(), n_elems, nb_maps, dleft.as<double>(),
+                                                                         dnb.as<uint32_t>(),
+                                                                         dhist.as<unsigned long long>(), unit_cap);
+        EAE_LAUNCH_OK();
+        EAE_CUDA_OK(cudaMemcpyAsync(unit_hist_out, dhist.p, (size_t)nb_maps * unit_cap * 8, cudaMemcpyDeviceToHost, st));
+        EAE_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (abs_counts_out) {
+        DevBuf dmean, ddelta, dcnt;
+        EAE_TRY(dmean.alloc((size_t)nb_maps * 4));
+        EAE_TRY(ddelta.alloc((size_t)nb_maps * 4));
+        EAE_TRY(dcnt.alloc((size_t)nb_maps * (L + 1u) * 8));
+        EAE_CUDA_OK(cudaMemcpyAsync(dmean.p, mean, (size_t)nb_maps * 4, cudaMemcpyHostToDevice, st));
+        EAE_CUDA_OK(cudaMemcpyAsync(ddelta.p, delta, (size_t)nb_maps * 4, cudaMemcpyHostToDevice, st));
+        EAE_CUDA_OK(cudaMemsetAsync(dcnt.p, 0, (size_t)nb_maps * (L + 1u) * 8, st));
+        const size_t smem = (size_t)(L + 1u) * nb_maps * 4;
+        if (smem > 200u * 1024u) { set_error("nb_maps * (L + 1) too large for the counting kernel"); return EAE_ERR_ARGUMENT; }
+        EAE_CUDA_OK(cudaFuncSetAttribute(stats_abs_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stats_abs_index_kernel<<<blocks, 256, smem, st>>>(dy.as<float>(), n_rows, nb_maps, dmean.as<float>(), ddelta.as<float>(), L,
+                                                          dcnt.as<unsigned long long>(), rows_per_block);
+        EAE_LAUNCH_OK();
+        EAE_CUDA_OK(cudaMemcpyAsync(abs_counts_out, dcnt.p, (size_t)nb_maps * (L + 1u) * 8, cudaMemcpyDeviceToHost, st));
+        EAE_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}

@@ -209,6 +209,24 @@ int eae_sum_squared_error_u8_host(const uint8_t* a, const uint8_t* b, uint64_t n
 int eae_count_nb_deads_host(const float* data, uint32_t n, uint64_t hw, uint32_t nb_maps,
                             uint32_t* nb_deads, void* stream);
 
+/*
+ * The counting part of lossless.stats.save_statistics (lossless/stats.py:13-68, 70-134, 136-195, 197-241,
+ * 243-320) over a calibration set of latents y: float32 [n_rows, nb_maps] (an NHWC batch, flattened).
+ *   sum_out  float64 [nb_maps]: per-map sum (map_mean = sum / n_rows, :311)
+ *   min_out, max_out float32 [nb_maps]
+ *   unit_hist_out (may be NULL) uint64 [nb_maps, unit_cap]: numpy.histogram of map c with unit bins from
+ *     floor(min) to ceil(max) (compute_probabilities_intervals with size_interval 1, used by
+ *     find_index_map_exception); needed_cap (may be NULL) receives the widest range; EAE_ERR_ARGUMENT if it
+ *     exceeds unit_cap
+ *   abs_counts_out (may be NULL) uint64 [nb_maps, L + 1]: occurrences of a = min(|rint((y - mean) / delta)|, L)
+ *     in float32 arithmetic, from which count_binary_decisions follows: zeros[j] = counts[j],
+ *     ones[j] = sum of counts[j + 1 ..]
+ */
+int eae_latent_statistics_host(const float* y, uint64_t n_rows, uint32_t nb_maps, double* sum_out,
+                               float* min_out, float* max_out, uint64_t* unit_hist_out, uint32_t unit_cap,
+                               uint32_t* needed_cap, const float* mean, const float* delta,
+                               uint32_t truncated_unary_length, uint64_t* abs_counts_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Transforms                                                                                  */
 

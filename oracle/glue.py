@@ -118,3 +118,30 @@ def binary_probabilities_from_counts(zeros, ones):
     p[p == 0.] = 0.01
     p[p == 1.] = 0.99
     return p
+
+
+def probabilities_unit_intervals(data):
+    """stats.py:70-134 with size_interval 1: numpy.histogram over unit bins from floor(min) to ceil(max)."""
+    left = numpy.floor(numpy.amin(data)).item()
+    right = numpy.ceil(numpy.amax(data)).item()
+    if right - left < 1.:
+        raise ValueError('The interval size exceeds the range of the data values.')
+    edges = numpy.linspace(left, right, num=int(right - left) + 1)
+    return (edges, numpy.histogram(data, bins=edges, density=True)[0]*1.)
+
+
+def jensen_shannon_divergence(probs_0, probs_1):
+    """tools.py:615-666."""
+    denominator = 0.5*(probs_0 + probs_1)
+    return 0.5*numpy.sum(probs_0*numpy.log2(probs_0/denominator) + probs_1*numpy.log2(probs_1/denominator))
+
+
+def find_index_map_exception(y_float32):
+    """stats.py:197-241: the map whose unit-interval histogram is closest (Jensen-Shannon) to uniform."""
+    nb_maps = y_float32.shape[3]
+    divergences = numpy.zeros(nb_maps)
+    for i in range(nb_maps):
+        probs = probabilities_unit_intervals(y_float32[:, :, :, i])[1]
+        nz = numpy.extract(probs != 0., probs)
+        divergences[i] = jensen_shannon_divergence(nz, numpy.ones(nz.size)/nz.size) if nz.size > 1 else 1.
+    return numpy.argmin(divergences).item()

@@ -54,3 +54,81 @@ def test_psnr_entropy_rate_deads(tls, golden):
     assert tls.count_nb_deads(numpy.zeros((2, 3, 3, 4), dtype=numpy.float32)).tolist() == [4, 4]
     with pytest.raises(AssertionError):     # "The quantization was omitted." (tools.py:372-375)
         tls.rate_3d((q[0] + 0.3).astype(numpy.float32), bw, 192, 320)
+
+
+@pytest.fixture(scope='module')
+def stats(native):
+    from autoencoder_based_image_compression_b200.kodak_tensorflow.lossless import stats
+    return stats
+
+
+def test_statistics_match_the_reference_outputs(stats, golden):
+    """lossless.stats on the GPU against the reference's own outputs on the same seeded latents (glue.npz):
+    tables bit-identical, same exception map, known answers of test_lossless.py:267-298."""
+    g = golden.load('glue')
+    data = g['quantize__data']
+    bw = g['quantize__bin_widths']
+    table = stats.compute_binary_probabilities(data, bw, g['binary_probabilities__mean'], 10)
+    assert table.dtype == numpy.float64 and numpy.array_equal(table, g['binary_probabilities__out'])
+    assert stats.find_index_map_exception(data) == int(g['idx_map_exception__out'])
+    (z, o) = stats.count_binary_decisions(numpy.array([0.75, 0.05, 0.1, 0.2, 0.2, 0.15], dtype=numpy.float32), 0.05, 7)
+    assert numpy.array_equal(numpy.stack([z, o]), g['binary_decisions__0'])
+    (z, o) = stats.count_binary_decisions(numpy.array([210., 6., 9., 6.], dtype=numpy.float32), 3., 7)
+    assert numpy.array_equal(numpy.stack([z, o]), g['binary_decisions__1'])
+    with pytest.raises(ValueError):
+        stats.count_binary_decisions(numpy.array([1., -1.], dtype=numpy.float32), 1., 4)
+
+
+def test_statistics_against_the_oracle_on_wide_and_degenerate_maps(stats):
+    rng = numpy.random.default_rng(5)
+    y = (rng.laplace(0., 2., size=(5, 16, 24, 128))*rng.uniform(0.05, 30., size=128)).astype(numpy.float32)
+    y[..., 3] = rng.uniform(-40., 40., size=y.shape[:3])         # the near-uniform map
+    y[..., 7] = 0.25                                             # a constant map inside one unit interval
+    y[..., 9] = rng.integers(-3, 4, size=y.shape[:3])            # values on the interval edges, maximum on the right edge
+    mean = numpy.mean(y, axis=(0, 1, 2)).astype(numpy.float32)
+    bw = rng.uniform(0.3, 4., size=128).astype(numpy.float32)
+    for L in (1, 10, 40):
+        cq = oracle_glue.quantize_per_map(y - mean.reshape((1, 1, 1, -1)), bw)
+        want = numpy.stack([oracle_glue.binary_probabilities_from_counts(
+            *oracle_glue.count_binary_decisions(numpy.absolute(cq[..., i]), float(bw[i]), L)) for i in range(128)])
+        assert numpy.array_equal(stats.compute_binary_probabilities(y, bw, mean, L), want), L
+    assert stats.find_index_map_exception(y) == oracle_glue.find_index_map_exception(y) == 3
+    (edges, probs) = stats.compute_probabilities_intervals(y[..., 9], 1.)
+    (want_edges, want_probs) = oracle_glue.probabilities_unit_intervals(y[..., 9])
+    assert numpy.array_equal(edges, want_edges) and numpy.array_equal(probs, want_probs)
+    with pytest.raises(ValueError):      # stats.py:105-106: all values equal to one integer
+        stats.find_index_map_exception(numpy.full((1, 2, 2, 128), 2., dtype=numpy.float32))
+
+
+def test_save_statistics_writes_the_three_kinds_of_files(stats, native, tmp_path):
+    from autoencoder_based_image_compression_b200 import codec as native_codec
+    from autoencoder_based_image_compression_b200.kodak_tensorflow.eae.graph.EntropyAutoencoder import EntropyAutoencoder
+    from oracle import transforms as oracle_transforms
+    from tests import util
+    rng = numpy.random.default_rng(11)
+    lum = util.synthetic_luma(rng, 4, 64, 96)[..., None]
+    multipliers = numpy.array([1., 2.], dtype=numpy.float32)
+    paths = [str(tmp_path/'binary_probabilities_{}.npy'.format(i)) for i in range(2)]
+    (p_mean, p_idx) = (str(tmp_path/'map_mean.npy'), str(tmp_path/'idx_map_exception.pkl'))
+    entropy_ae = EntropyAutoencoder(2, 64, 96, 1., 10000., '', False)
+    with native_codec.Session(device=0, math='tf32x3') as sess:
+        entropy_ae.initialization(sess, '')
+        stats.save_statistics(lum, sess, entropy_ae, 2, multipliers, 10, p_mean, p_idx, paths)
+        y = __import__('autoencoder_based_image_compression_b200.kodak_tensorflow.eae.batching', fromlist=['x']) \
+            .encode_mini_batches(lum, sess, entropy_ae, 2)
+    import pickle
+    map_mean = numpy.load(p_mean)
+    assert map_mean.dtype == numpy.float32 and numpy.array_equal(map_mean, numpy.mean(y, axis=(0, 1, 2)))
+    with open(p_idx, 'rb') as f:
+        assert pickle.load(f) == oracle_glue.find_index_map_exception(y)
+    for (i, path) in enumerate(paths):
+        table = numpy.load(path)
+        assert table.shape == (128, 10) and table.dtype == numpy.float64
+        assert table.min() >= 0.01 and table.max() <= 0.99
+        bw = multipliers[i]*entropy_ae.get_bin_widths()
+        cq = oracle_glue.quantize_per_map(y - map_mean.reshape((1, 1, 1, -1)), bw)
+        want = numpy.stack([oracle_glue.binary_probabilities_from_counts(
+            *oracle_glue.count_binary_decisions(numpy.absolute(cq[..., j]), float(bw[j]), 10)) for j in range(128)])
+        assert numpy.array_equal(table, want)
+    with pytest.raises(ValueError):      # stats.py:296-297
+        stats.save_statistics(lum, None, entropy_ae, 2, multipliers, 10, p_mean, p_idx, paths[:1])

@@ -166,11 +166,29 @@ def test_drop_in_module_names_resolve(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import sys; sys.path.insert(0, {root!r}); "
             "sys.path.insert(0, {root!r} + '/autoencoder_based_image_compression_b200/kodak_tensorflow'); "
-            "import eae.batching, lossless.compression, lossless.interface_cython, tools.tools as tls; "
+            "import eae.batching, lossless.compression, lossless.interface_cython, lossless.stats, tools.tools as tls; "
             "from eae.graph.EntropyAutoencoder import EntropyAutoencoder; "
             "from eae.graph.IsolatedDecoder import IsolatedDecoder; "
             "import eae.graph.constants as csts; "
             "assert csts.STRIDE_PROD == 16 and callable(eae.batching.encode_mini_batches) "
-            "and callable(lossless.compression.rescale_compress_lossless_maps) and callable(tls.quantize_per_map)"
+            "and callable(lossless.compression.rescale_compress_lossless_maps) and callable(tls.quantize_per_map) "
+            "and callable(lossless.stats.save_statistics) and callable(lossless.stats.find_index_map_exception)"
             ).format(root=root)
     subprocess.check_call([sys.executable, '-c', code], cwd=str(tmp_path))
+
+
+def test_statistics_argument_checks(tmp_path):
+    """lossless/stats.py checks that do not need the device."""
+    from autoencoder_based_image_compression_b200.kodak_tensorflow.lossless import stats
+    y = numpy.zeros((1, 2, 2, 128), dtype=numpy.float32)
+    with pytest.raises(TypeError):
+        stats.compute_binary_probabilities(y.astype(numpy.float64), numpy.ones(128), numpy.zeros(128), 10)
+    with pytest.raises(ValueError):
+        stats.compute_binary_probabilities(y, numpy.zeros(128), numpy.zeros(128), 10)      # bin width 0
+    with pytest.raises(ValueError):
+        stats.count_binary_decisions(numpy.array([0.5, -0.5], dtype=numpy.float32), 0.5, 4)
+    with pytest.raises(ValueError):      # stats.py:296-297
+        stats.save_statistics(None, None, None, 1, numpy.ones(2), 10, str(tmp_path/'a.npy'), str(tmp_path/'b.pkl'), ['x.npy'])
+    with pytest.raises(ValueError):      # tools.py:652-653
+        stats.jensen_shannon_divergence(numpy.array([0., 1.]), numpy.array([0.5, 0.5]))
+    assert abs(stats.jensen_shannon_divergence(numpy.array([0.5, 0.5]), numpy.array([0.5, 0.5]))) < 1e-15
