@@ -296,7 +296,7 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     // stride-2 layer that follows. On the tensor path (kernel version 3) the patches are gathered from the uint8
     // image inside the kernel; otherwise an im2col pass writes them out first.
     {
-        const bool direct = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() == 3 &&
+        const bool direct = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() >= 3 &&
                             !c->no_direct_conv1;
         if (!direct) { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);

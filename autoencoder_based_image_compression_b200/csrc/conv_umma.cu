@@ -139,6 +139,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (elect.sync): the MMA warp runs its loop with all lanes and issues from the elected
+// one, so that every tcgen05 operand is a warp-uniform value (see the note on kTmemBase0).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -699,6 +707,7 @@ constexpr int kImgBytes = ((kImgBoxW * kImgBoxH + 127) / 128) * 128;
 constexpr int kSmemBytes3 = kStages3 * kStageBytes3 + kImgBytes + 1024 + 256;
 constexpr int kUmmaThreads3 = 320;
 constexpr uint32_t kCol3Acc0 = 0, kCol3Acc1 = 128, kCol3Slots = 256, kCol3Nrm0 = 256, kCol3Nrm1 = 384;
+constexpr uint32_t kTmemBase0 = 0;      // TMEM address of a 512-column allocation on an otherwise empty SM
 
 // 32 consecutive im2col entries (k = ky * 9 + kx, chunk kChunk of three) of one 9x9 uint8 patch as fp32 bit
 // patterns: a byte b becomes 0x4B0000bb = 2^23 + b, minus 2^23 (exact).
@@ -770,6 +779,10 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // This CTA owns the whole TMEM of its SM (512 columns, 1 CTA per SM), so the allocation starts at column 0. The
+    // MMA-issuing thread uses that CONSTANT: with the base read from shared memory every tcgen05.mma operand went
+    // through an ELECT / R2UR / BRA.U.ANY waterfall (~80 cycles of issue per MMA, more than the 64 it executes).
+    if (tmem_base != kTmemBase0 && threadIdx.x == 0) atomicOr(p.error_flag, 1u << 8);
     if (stamp && threadIdx.x == 64) stamp[1] = clock64();
 
     const int n_main = p.n_taps * p.kchunks;
@@ -811,18 +824,19 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            for (int it = 0; it < n_total; it++) {
-                const int s = it % kStages3;
-                if (!mbar_wait(&split[s], (it / kStages3) & 1, p.error_flag, 1)) break;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (warp-uniform operands) =====
+        for (int it = 0; it < n_total; it++) {
+            const int s = it % kStages3;
+            const bool ok = __all_sync(0xFFFFFFFFu, mbar_wait(&split[s], (it / kStages3) & 1, p.error_flag, 1));
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
                 const uint32_t st = smem_u32(smem + s * kStageBytes3);
                 if (it < n_main) {
-                    const uint32_t slot = tmem_base + kCol3Slots + 128u * (uint32_t)(it & 1);
+                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)(it & 1);
                     #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const uint32_t d = tmem_base + (h ? kCol3Acc1 : kCol3Acc0);
+                        const uint32_t d = kTmemBase0 + (h ? kCol3Acc1 : kCol3Acc0);
                         const uint32_t a_hi = slot + 64u * (uint32_t)h, a_lo = a_hi + 32u;
                         #pragma unroll
                         for (int k = 0; k < kChunkK / 8; k++) {
@@ -835,7 +849,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 } else {
                     // fused GDN: NRM_h += (x^2)_hi g_hi + (x^2)_lo g_hi + (x^2)_hi g_lo, operands in shared memory
                     const int g = it - n_main, h = g >> 2, kc = g & 3;
-                    const uint32_t d = tmem_base + (h ? kCol3Nrm1 : kCol3Nrm0);
+                    const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
                     #pragma unroll
                     for (int k = 0; k < kChunkK / 8; k++) {
                         const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
@@ -849,6 +863,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
                 if (n_gdn && it == n_total - 1) umma_commit(nrm_full);
             }
+            __syncwarp();
         }
     } else {
         // ===== warps 2..9: two conversion / epilogue sets (set = iteration parity) =====
@@ -1045,6 +1060,383 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// =================================================================================================
+// Version 4 (default for the multi-tap layers): version 3 with every activation box fetched ONCE.
+//
+// Measured on version 3 (profiles/r01_ncu_full_gemm_umma3_layers.md): a ring iteration of a k5 layer moves
+// 64 KB from L2 into shared memory (two 16 KB activation boxes + 32 KB of split weights) for 24 MMAs, i.e.
+// the kernel asks for ~42 B/clk/SM against an L2 throughput cap of ~43 B/clk/SM (6.3 KB/clk over 148 SMs),
+// and the conversion warps spend 38 % of their samples waiting for TMA data: iterations take 1.95 k cycles
+// instead of the 1.54 k the MMAs need. But the boxes of the taps of one input plane are the same pixels shifted
+// by one position: the 9 taps of the (odd, odd) parity plane of a k5 s2 convolution overlap in 15/16 of their
+// rows. Here the loop runs channel chunk -> tap group -> tap, the UNION box of a group (18 x 18 positions x 32
+// channels, 41 KB) is loaded once into one of two buffers, and the conversion warps read each tap's rows from
+// it at a shifted offset; only the weights stream per tap (32 KB stages, 4 deep). Activation traffic drops from
+// 3.2 MB to 0.65 MB per 256-position tile of a 25-tap layer (total L2 -> SM traffic -40 %).
+//
+//  smem: union buffers 2 x 41 KB | weight stages 4 x { B_hi 16K | B_lo 16K } | barriers. The fused GDN phase and
+//        the epilogue alias the first 192 KB as in version 3 (3 stages x 64 KB), after the main loop has drained.
+constexpr int kUnionW = 18, kUnionH = 18;
+constexpr int kUnionTx = kUnionW * kUnionH * 128;          // bytes one union load delivers
+constexpr int kUnionBytes = 41 * 1024;
+constexpr int kBStages4 = 4, kBStageBytes4 = 2 * kTileBytes;
+constexpr int kOffB4 = 2 * kUnionBytes;
+constexpr int kOffBars4 = kOffB4 + kBStages4 * kBStageBytes4;
+constexpr int kSmemBytes4 = kOffBars4 + 256 + 1024;
+constexpr int kGdnStageBytes4 = 4 * kTileBytes;
+static_assert(3 * kGdnStageBytes4 <= kOffBars4, "GDN / epilogue stages must fit below the barriers");
+constexpr int kMaxGroups4 = 4;
+
+struct UmmaTap4 { int w_tap, off, grp, last; };            // off: row offset of this tap's box inside its group's union
+struct UmmaGroup4 { int plane, fy, fx, pad; };             // union origin relative to the tile origin
+struct UmmaParams4 {
+    int n_taps, kchunks, n_groups;
+    int tiles_x, tiles_y, Hg, Wg;
+    float* out;
+    const float* bias;
+    const float* beta;
+    int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int fuse, exact_main;
+    long long* times;
+    uint32_t* error_flag;
+    UmmaTap4 taps[kMaxTaps];
+    UmmaGroup4 groups[kMaxGroups4];
+};
+
+__global__ void __launch_bounds__(kUmmaThreads3, 1)
+gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
+                  const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4 p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars4);
+    uint64_t* b_full = bars;               // [4] weight stage landed
+    uint64_t* done = bars + 4;             // [4] the MMAs of iteration it (it & 3) completed: ONE commit per iteration
+                                           //     releases the weight stage (it + 4), the TMEM A slot (it + 2) and, after the
+                                           //     last tap of a group, its union buffer (a tcgen05.commit costs ~100 cycles of
+                                           //     tensor-pipe time, three per iteration made the loop 15 % slower)
+    uint64_t* u_full = bars + 8;           // [2] union box landed
+    uint64_t* split = bars + 12;           // [2] TMEM A slot written (128 arrivals: one conversion set)
+    uint64_t* acc_full = bars + 16;
+    uint64_t* g_full = bars + 17;          // [3] fused GDN ring
+    uint64_t* g_split = bars + 20;
+    uint64_t* g_empty = bars + 23;
+    uint64_t* nrm_full = bars + 26;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
+    if (stamp && threadIdx.x == 64) stamp[0] = clock64();
+    // tile = 16 x 16 positions: half h covers rows [a0 + 8 h, + 8)
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&u_full[s], 1); mbar_init(&split[s], 4); }     // one arrival per conversion warp
+        for (int s = 0; s < 3; s++) { mbar_init(&g_full[s], 1); mbar_init(&g_split[s], 4); mbar_init(&g_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(nrm_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // This CTA owns the whole TMEM of its SM (512 columns, 1 CTA per SM), so the allocation starts at column 0. The
+    // MMA-issuing thread uses that CONSTANT: with the base read from shared memory every tcgen05.mma operand went
+    // through an ELECT / R2UR / BRA.U.ANY waterfall (~80 cycles of issue per MMA, more than the 64 it executes).
+    if (tmem_base != kTmemBase0 && threadIdx.x == 0) atomicOr(p.error_flag, 1u << 8);
+    if (stamp && threadIdx.x == 64) stamp[1] = clock64();
+
+    const int n_main = p.n_taps * p.kchunks;      // iteration it = kc * n_taps + t
+    const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
+    const int n_unions = p.kchunks * p.n_groups;  // union g = kc * n_groups + group
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            bool ok = true;
+            int issued = 0;                       // unions requested so far
+            for (int it = 0; it < n_main && ok; it++) {
+                const int kc = it / p.n_taps, t = it - kc * p.n_taps;
+                const UmmaTap4 tap = p.taps[t];
+                const int g = kc * p.n_groups + tap.grp;
+                // the union this tap reads, and (without waiting) the one after it as soon as its buffer is free
+                while (ok && issued < n_unions && issued <= g + 1) {
+                    const int buf = issued & 1;
+                    if (issued >= 2) {
+                        // the buffer held union issued - 2: free once the MMAs of that group's last tap are done
+                        const int pk = (issued - 2) / p.n_groups, pg = (issued - 2) - pk * p.n_groups;
+                        const int last_it = pk * p.n_taps + p.groups[pg].pad;      // pad = index of the group's last tap
+                        const uint32_t par = (uint32_t)(last_it >> 2) & 1u;
+                        if (issued <= g) ok = mbar_wait(&done[last_it & 3], par, p.error_flag, 0);
+                        else if (!mbar_try(&done[last_it & 3], par)) break;
+                        if (!ok) break;
+                    }
+                    const UmmaGroup4 grp = p.groups[issued % p.n_groups];
+                    mbar_expect_tx(&u_full[buf], kUnionTx);
+                    tma_load_5d(smem + buf * kUnionBytes, &map_u, &u_full[buf], (issued / p.n_groups) * kChunkK, b0 + grp.fx,
+                                a0 + grp.fy, grp.plane, img);
+                    issued++;
+                }
+                if (!ok) break;
+                const int s = it & 3;
+                if (!mbar_wait(&done[s], ((uint32_t)(it >> 2) & 1u) ^ 1u, p.error_flag, 0)) { ok = false; break; }
+                uint8_t* st = smem + kOffB4 + s * kBStageBytes4;
+                mbar_expect_tx(&b_full[s], (p.exact_main ? 2 : 1) * kTileBytes);
+                tma_load_3d(st, &map_b_hi, &b_full[s], kc * kChunkK, 0, tap.w_tap);
+                if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &b_full[s], kc * kChunkK, 0, tap.w_tap);
+            }
+            if (ok && n_gdn) {
+                // the GDN stages alias the main-loop buffers: wait until every main MMA has completed
+                ok = mbar_wait(acc_full, 0, p.error_flag, 0);
+                for (int j = 0; j < n_gdn && ok; j++) {
+                    const int s = j % 3;
+                    ok = mbar_wait(&g_empty[s], ((uint32_t)(j / 3) & 1u) ^ 1u, p.error_flag, 0);
+                    if (!ok) break;
+                    uint8_t* st = smem + s * kGdnStageBytes4;
+                    mbar_expect_tx(&g_full[s], 2 * kTileBytes);
+                    tma_load_3d(st + 2 * kTileBytes, &map_g_hi, &g_full[s], (j & 3) * kChunkK, 0, 0);
+                    tma_load_3d(st + 3 * kTileBytes, &map_g_lo, &g_full[s], (j & 3) * kChunkK, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+        {
+            bool ok = true;
+            for (int it = 0; it < n_main && ok; it++) {
+                const int slot_i = it & 1, s = it & 3;
+                ok = mbar_wait(&split[slot_i], (uint32_t)(it >> 1) & 1u, p.error_flag, 1);
+                if (ok) ok = mbar_wait(&b_full[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
+                ok = __all_sync(0xFFFFFFFFu, ok);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smem + kOffB4 + s * kBStageBytes4);
+                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i;
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t d = kTmemBase0 + (h ? kCol3Acc1 : kCol3Acc0);
+                        const uint32_t a_hi = slot + 64u * (uint32_t)h, a_lo = a_hi + 32u;
+                        #pragma unroll
+                        for (int k = 0; k < kChunkK / 8; k++) {
+                            const uint64_t b_hi = make_desc(st + k * 32);
+                            umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
+                            if (p.exact_main) {
+                                umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
+                                umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&done[s]);
+                    if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
+                }
+                __syncwarp();
+            }
+            for (int j = 0; j < n_gdn && ok; j++) {
+                // fused GDN: NRM_h += (x^2)_hi g_hi + (x^2)_lo g_hi + (x^2)_hi g_lo, operands in shared memory
+                const int s = j % 3, h = j >> 2, kc = j & 3;
+                ok = mbar_wait(&g_split[s], (uint32_t)(j / 3) & 1u, p.error_flag, 1);
+                ok = __all_sync(0xFFFFFFFFu, ok);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smem + s * kGdnStageBytes4);
+                    const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
+                    #pragma unroll
+                    for (int k = 0; k < kChunkK / 8; k++) {
+                        const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
+                        const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
+                        umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
+                        umma_tf32(d, x_lo, g_hi, 1u);
+                        umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
+                    }
+                    umma_commit(&g_empty[s]);
+                    if (j == n_gdn - 1) umma_commit(nrm_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== warps 2..9: two conversion / epilogue sets; set k owns TMEM A slot k and the iterations of parity k
+        const int quarter = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t slot = lane_base + kCol3Slots + 128u * (uint32_t)set;
+        const int row_in_union = (row >> 4) * kUnionW + (row & 15);     // half 1 adds 8 union rows
+        bool ok = true;
+        uint32_t r[32], hi[32];
+        for (int it = set; it < n_main && ok; it += 2) {
+            const int kc = it / p.n_taps, t = it - kc * p.n_taps;
+            const UmmaTap4 tap = p.taps[t];
+            const int g = kc * p.n_groups + tap.grp;
+            ok = mbar_wait(&u_full[g & 1], (uint32_t)(g >> 1) & 1u, p.error_flag, 2);
+            if (!ok) break;
+            if (stamp && it == 0 && threadIdx.x == 64) stamp[2] = clock64();
+            // Read both halves' rows first: the shared-memory reads do not depend on the TMEM slot, so they overlap the
+            // wait for the MMAs of iteration it - 2 (the completion -> conversion -> issue chain paces the loop).
+            const uint8_t* ubuf = smem + (g & 1) * kUnionBytes;
+            #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int ur = row_in_union + h * 8 * kUnionW + tap.off;
+                const uint8_t* rowp = ubuf + ur * 128;
+                uint32_t* dst = h ? hi : r;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (ur & 7)) << 4));
+                    dst[4 * c + 0] = __float_as_uint(v.x); dst[4 * c + 1] = __float_as_uint(v.y);
+                    dst[4 * c + 2] = __float_as_uint(v.z); dst[4 * c + 3] = __float_as_uint(v.w);
+                }
+            }
+            if (it >= 2) {      // the MMAs of iteration it - 2 read this slot
+                ok = mbar_wait(&done[(it - 2) & 3], (uint32_t)((it - 2) >> 2) & 1u, p.error_flag, 5);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x)
+            tmem_st32(slot, r);
+            tmem_st32(slot + 64u, hi);
+            if (p.exact_main) {
+                #pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
+                    hi[i] = __float_as_uint(__uint_as_float(hi[i]) - __uint_as_float(hi[i] & 0xFFFFE000u));
+                }
+                tmem_st32(slot + 32u, r);
+                tmem_st32(slot + 96u, hi);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[set]);      // 4 arrivals instead of 128: the arrive chain is on the critical path
+        }
+        for (int j = set; j < n_gdn && ok; j += 2) {
+            const int s = j % 3;
+            uint8_t* st = smem + s * kGdnStageBytes4;
+            if (j < 2) {      // first GDN chunk of this set: the accumulators are final (and the main buffers free)
+                ok = mbar_wait(acc_full, 0, p.error_flag, 3);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (stamp && threadIdx.x == 64) stamp[4] = clock64();
+            }
+            // the x^2 operands go to the A part of the stage: wait until the MMAs of its previous use are done
+            ok = mbar_wait(&g_empty[s], ((uint32_t)(j / 3) & 1u) ^ 1u, p.error_flag, 7);
+            if (!ok) break;
+            const int h = j >> 2, c0 = (j & 3) * kChunkK;
+            tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
+            uint8_t* rowp = st + row * 128;
+            #pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                       __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                if (p.bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
+                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                }
+                x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
+                float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
+                xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
+                *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            // the MMA also needs gamma: it waits for g_split only, so this set vouches for the TMA data too
+            ok = mbar_wait(&g_full[s], (uint32_t)(j / 3) & 1u, p.error_flag, 2);
+            if (!ok) break;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&g_split[s]);
+        }
+        if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+
+        // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (four swizzled [128 x 32]
+        // sub-tiles per half) -> coalesced 512-byte rows.
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            uint8_t* stage = smem + h * kGdnStageBytes4;
+            #pragma unroll 1
+            for (int cc = 0; cc < 2; cc++) {
+                const int c0 = set * 64 + cc * 32;
+                tmem_ld32_nowait(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                if (n_gdn) tmem_ld32_nowait(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
+                tmem_ld_wait();
+                uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                    if (p.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    }
+                    if (n_gdn) {
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * c));
+                        const float n0 = __uint_as_float(hi[4 * c]) + be.x, n1 = __uint_as_float(hi[4 * c + 1]) + be.y;
+                        const float n2 = __uint_as_float(hi[4 * c + 2]) + be.z, n3 = __uint_as_float(hi[4 * c + 3]) + be.w;
+                        if (p.fuse == 1) {
+                            v.x *= rsqrtf(n0); v.y *= rsqrtf(n1); v.z *= rsqrtf(n2); v.w *= rsqrtf(n3);
+                        } else {
+                            v.x *= n0 * rsqrtf(n0); v.y *= n1 * rsqrtf(n1); v.z *= n2 * rsqrtf(n2); v.w *= n3 * rsqrtf(n3);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = v;
+                }
+            }
+        }
+        named_bar_sync(1, 256);     // both sets finished staging
+        if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+        const int wq = warp - 2;
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const uint8_t* stage = smem + h * kGdnStageBytes4;
+            #pragma unroll 1
+            for (int j0 = 0; j0 < kTileM / 8; j0 += 4) {
+                float4 v[4];
+                float* dst[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int rr = wq + 8 * (j0 + j);
+                    const int a = a0 + h * 8 + (rr >> 4), b = b0 + (rr & 15);
+                    const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
+                    size_t opix;
+                    if (p.out_split)
+                        opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
+                    else
+                        opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+                    dst[j] = (ok && a < p.Hg && b < p.Wg) ? p.out + opix * kCout + lane * 4 : nullptr;
+                    v[j] = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 +
+                                                            (((lane & 7) ^ (rr & 7)) << 4));
+                }
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (dst[j]) *reinterpret_cast<float4*>(dst[j]) = v[j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (stamp && threadIdx.x == 64) stamp[7] = clock64();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1137,8 +1529,8 @@ int umma_version()
     static int v = 0;
     if (!v) {
         const char* env = getenv("EAE_UMMA_VERSION");
-        v = env ? atoi(env) : 3;
-        if (v < 1 || v > 3) v = 3;
+        v = env ? atoi(env) : 4;
+        if (v < 1 || v > 4) v = 4;
     }
     return v;
 }
@@ -1194,7 +1586,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
     if (plan.img_u8) {
-        if (umma_version() != 3 || plan.n_taps != 1 || plan.Cin != 96 || plan.Hg * 4 != plan.img_H ||
+        if (umma_version() < 3 || plan.n_taps != 1 || plan.Cin != 96 || plan.Hg * 4 != plan.img_H ||
             plan.Wg * 4 != plan.img_W || plan.img_W % 16 != 0) {
             set_error("gemm_umma: the fused k9 s4 convolution needs kernel version 3 and a [n, 4 Hg, 4 Wg] image");
             return EAE_ERR_ARGUMENT;
@@ -1206,7 +1598,97 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         EAE_TRY(make_map(&map_a, plan.in, 5, adims, abox));
     }
     const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
-    if (umma_version() == 3) {
+    if (umma_version() >= 4 && plan.n_taps > 1 && plan.Hg > 1 && plan.Cin == 128 && !plan.img_u8) {
+        // ---- version 4: tap groups that share one input plane read their boxes from one union box ----
+        UmmaParams4 q;
+        memset(&q, 0, sizeof q);
+        q.n_taps = plan.n_taps; q.kchunks = plan.Cin / kChunkK;
+        q.tiles_x = (plan.Wg + 15) / 16; q.tiles_y = (plan.Hg + 15) / 16;
+        q.Hg = plan.Hg; q.Wg = plan.Wg;
+        q.out = plan.out; q.bias = plan.bias; q.beta = plan.fuse_beta;
+        q.Hout = plan.Hout; q.Wout = plan.Wout; q.out_mul = plan.out_mul; q.out_r = plan.out_r; q.out_s = plan.out_s;
+        q.out_split = plan.out_split;
+        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0;
+        q.error_flag = g_error_flag;
+        // groups = input planes in use; taps sorted by group
+        int fy_min[kMaxGroups4], fx_min[kMaxGroups4], fy_max[kMaxGroups4], fx_max[kMaxGroups4], group_of_plane[4] = {-1, -1, -1, -1};
+        int n_groups = 0;
+        for (int t = 0; t < plan.n_taps; t++) {
+            const UmmaTap& u = p.taps[t];
+            int g = group_of_plane[u.plane];
+            if (g < 0) {
+                g = group_of_plane[u.plane] = n_groups++;
+                fy_min[g] = fy_max[g] = u.fy; fx_min[g] = fx_max[g] = u.fx;
+            }
+            if (u.fy < fy_min[g]) fy_min[g] = u.fy;
+            if (u.fy > fy_max[g]) fy_max[g] = u.fy;
+            if (u.fx < fx_min[g]) fx_min[g] = u.fx;
+            if (u.fx > fx_max[g]) fx_max[g] = u.fx;
+        }
+        bool fits = true;
+        for (int g = 0; g < n_groups; g++) fits = fits && fy_max[g] - fy_min[g] <= kUnionH - 16 && fx_max[g] - fx_min[g] <= kUnionW - 16;
+        if (fits && plan.mode == kEpiBias) {
+            q.n_groups = n_groups;
+            int nt = 0;
+            for (int g = 0; g < n_groups; g++) {
+                int plane = 0;
+                for (int pl = 0; pl < 4; pl++) if (group_of_plane[pl] == g) plane = pl;
+                q.groups[g] = UmmaGroup4{plane, fy_min[g], fx_min[g], 0};
+                for (int t = 0; t < plan.n_taps; t++) {
+                    const UmmaTap& u = p.taps[t];
+                    if (group_of_plane[u.plane] != g) continue;
+                    q.taps[nt++] = UmmaTap4{u.w_tap, (u.fy - fy_min[g]) * kUnionW + (u.fx - fx_min[g]), g, 0};
+                }
+                q.taps[nt - 1].last = 1;
+                q.groups[g].pad = nt - 1;      // index of the group's last tap in the sorted list
+            }
+            CUtensorMap map_u;
+            const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
+            const uint32_t ubox[5] = {kChunkK, (uint32_t)kUnionW, (uint32_t)kUnionH, 1, 1};
+            EAE_TRY(make_map(&map_u, plan.in, 5, adims, ubox));
+            CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo;
+            if (plan.fuse) {
+                if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta) {
+                    set_error("gemm_umma: fused GDN needs gamma hi/lo and beta");
+                    return EAE_ERR_ARGUMENT;
+                }
+                const uint64_t gdims[3] = {kCout, kCout, 1};
+                EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
+                EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
+            }
+            static bool attr4_done = false;
+            if (!attr4_done) {
+                EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+                attr4_done = true;
+            }
+            const uint32_t grid4 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
+            static int timing4 = -1;
+            if (timing4 < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing4 = e ? atoi(e) : 0; }
+            long long* d_times = nullptr;
+            if (timing4) {
+                EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid4 * 8 * sizeof(long long)));
+                EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * 8 * sizeof(long long), st));
+                q.times = d_times;
+            }
+            gemm_umma4_kernel<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+            EAE_LAUNCH_OK();
+            if (timing4) {
+                std::vector<long long> h((size_t)grid4 * 8);
+                EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+                EAE_CUDA_OK(cudaStreamSynchronize(st));
+                cudaFree(d_times);
+                double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (uint32_t b = 0; b < grid4; b++)
+                    for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 8 + j] - h[(size_t)b * 8]);
+                fprintf(stderr, "umma4 taps %d groups %d fuse %d grid %u: setup %.0f first_union %.0f acc_seen %.0f nrm_seen %.0f "
+                                "staged %.0f end %.0f (avg cycles from CTA start, conversion warp 2)\n",
+                        q.n_taps, q.n_groups, q.fuse, grid4, acc[1] / grid4, acc[2] / grid4, acc[4] / grid4, acc[5] / grid4,
+                        acc[6] / grid4, acc[7] / grid4);
+            }
+            return 0;
+        }
+    }
+    if (umma_version() >= 3) {
         UmmaParams2 q;
         memset(&q, 0, sizeof q);
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;

