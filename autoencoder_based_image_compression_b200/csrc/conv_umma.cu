@@ -732,6 +732,171 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// ---- fused GDN / IGDN tail shared by versions 3 and 4 --------------------------------------------------------
+// NRM_h = (x_h^2) gamma for both 128-row halves h, x = accumulator + bias, as 8 steps j = 4 h + kc over the four
+// 32-channel chunks of x^2. gamma (hi | lo, 4 x 32 KB) is loaded ONCE and stays resident; (x^2)_hi / (x^2)_lo of a
+// step go to one of two 32 KB buffers (conversion set k owns buffer k, as it owns TMEM slot k in the main loop),
+// all in the 192 KB that the main loop has just released:
+//   area + 0 / + 32K : X[0] / X[1] = { (x^2)_hi 16K | (x^2)_lo 16K }, canonical K-major SWIZZLE_128B tiles
+//   area + 64K + kc * 32K : gamma chunk kc = { hi 16K | lo 16K }
+struct GdnTail {
+    uint8_t* area;
+    uint64_t* g_full;      // [4] gamma chunk kc landed (single use)
+    uint64_t* x_ready;     // [2] x^2 buffer written (4 arrivals: one per conversion warp of the set)
+    uint64_t* x_free;      // [2] the MMAs that read the buffer completed
+    uint64_t* acc_full;
+    uint64_t* nrm_full;
+};
+__device__ __forceinline__ void gdn_tail_init(const GdnTail& t)
+{
+    for (int s = 0; s < 4; s++) mbar_init(&t.g_full[s], 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
+}
+// TMA producer thread, after its last main-loop load.
+__device__ __forceinline__ void gdn_tail_producer(const GdnTail& t, const CUtensorMap* map_g_hi, const CUtensorMap* map_g_lo,
+                                                  uint32_t* error_flag)
+{
+    // gamma lands on the buffers of the main loop: wait until every main MMA has completed
+    if (!mbar_wait(t.acc_full, 0, error_flag, 0)) return;
+    for (int kc = 0; kc < 4; kc++) {
+        uint8_t* g = t.area + 4 * kTileBytes + kc * 2 * kTileBytes;
+        mbar_expect_tx(&t.g_full[kc], 2 * kTileBytes);
+        tma_load_3d(g, map_g_hi, &t.g_full[kc], kc * kChunkK, 0, 0);
+        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[kc], kc * kChunkK, 0, 0);
+    }
+}
+// MMA warp (all lanes; one elected lane issues).
+__device__ __forceinline__ void gdn_tail_mma(const GdnTail& t, uint32_t* error_flag)
+{
+    for (int j = 0; j < 8; j++) {
+        const int h = j >> 2, kc = j & 3, buf = j & 1;
+        bool ok = mbar_wait(&t.x_ready[buf], (uint32_t)(j >> 1) & 1u, error_flag, 1);
+        if (ok) ok = mbar_wait(&t.g_full[kc], 0, error_flag, 1);
+        if (!__all_sync(0xFFFFFFFFu, ok)) return;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint32_t x = smem_u32(t.area + buf * 2 * kTileBytes);
+            const uint32_t g = smem_u32(t.area + 4 * kTileBytes + kc * 2 * kTileBytes);
+            const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
+            #pragma unroll
+            for (int k = 0; k < kChunkK / 8; k++) {
+                const uint64_t x_hi = make_desc(x + k * 32), x_lo = make_desc(x + kTileBytes + k * 32);
+                const uint64_t g_hi = make_desc(g + k * 32);
+                umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
+                umma_tf32(d, x_lo, g_hi, 1u);
+                umma_tf32(d, x_hi, make_desc(g + kTileBytes + k * 32), 1u);
+            }
+            umma_commit(&t.x_free[buf]);
+            if (j == 7) umma_commit(t.nrm_full);
+        }
+        __syncwarp();
+    }
+}
+// Conversion warps of set `set` (thread = accumulator row): steps j = set, set + 2, ...
+__device__ __forceinline__ bool gdn_tail_convert(const GdnTail& t, int set, int row, int lane, uint32_t lane_base,
+                                                 const float* __restrict__ bias, uint32_t* error_flag)
+{
+    if (!mbar_wait(t.acc_full, 0, error_flag, 3)) return false;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint8_t* rowp = t.area + set * 2 * kTileBytes + row * 128;
+    uint32_t ra[32], rb[32];
+    tmem_ld32_nowait(lane_base + kCol3Acc0 + set * kChunkK, ra);     // step j = set: half 0, chunk `set`
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
+        tmem_ld_wait();
+        uint32_t* r = (i & 1) ? rb : ra;
+        if (i < 3) {      // the accumulator chunk of this set's next step is read while this one is squared
+            const int j2 = j + 2;
+            tmem_ld32_nowait(lane_base + ((j2 >> 2) ? kCol3Acc1 : kCol3Acc0) + (j2 & 3) * kChunkK, (i & 1) ? ra : rb);
+        }
+        if (i >= 1) {     // the MMAs of step j - 2 read this buffer
+            if (!mbar_wait(&t.x_free[set], (uint32_t)(i - 1) & 1u, error_flag, 7)) return false;
+        }
+        #pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                   __uint_as_float(r[4 * c + 3]));
+            if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
+                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+            }
+            x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
+            float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
+            xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
+            *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t.x_ready[set]);
+    }
+    return true;
+}
+
+// Epilogue staging shared by versions 3 and 4: this thread's row, this set's 64 channels of both halves:
+// TMEM (accumulator and, when GDN / IGDN is fused, the norm accumulator) -> bias, normalisation -> shared memory
+// (half h at smem + h * stage_bytes, four swizzled [128 x 32] sub-tiles). The TMEM reads of the next 32-column
+// chunk are in flight while the current one is processed (TMEM reads run at 64 B/clk per SM and were the longest
+// part of the epilogue when every chunk waited for its own load).
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // x = norm + beta >= 2e-5: never denormal
+    return r;
+}
+__device__ __forceinline__ void stage_chunk(uint8_t* sub, int row, int c0, const uint32_t* r, const uint32_t* nr, bool gdn,
+                                            int fuse, const float* __restrict__ bias, const float* __restrict__ beta)
+{
+    #pragma unroll
+    for (int c = 0; c < 8; c++) {
+        float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                               __uint_as_float(r[4 * c + 3]));
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        if (gdn) {
+            // x * rsqrt(norm + beta) (GDN) or x * (n * rsqrt(n)) (IGDN): the 2-ulp MUFU forms; their error (2^-22) is
+            // below that of the 3xTF32 contraction that produced x.
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4 * c));
+            const float n0 = __uint_as_float(nr[4 * c]) + be.x, n1 = __uint_as_float(nr[4 * c + 1]) + be.y;
+            const float n2 = __uint_as_float(nr[4 * c + 2]) + be.z, n3 = __uint_as_float(nr[4 * c + 3]) + be.w;
+            if (fuse == 1) {
+                v.x *= rsqrt_fast(n0); v.y *= rsqrt_fast(n1); v.z *= rsqrt_fast(n2); v.w *= rsqrt_fast(n3);
+            } else {
+                v.x *= n0 * rsqrt_fast(n0); v.y *= n1 * rsqrt_fast(n1); v.z *= n2 * rsqrt_fast(n2); v.w *= n3 * rsqrt_fast(n3);
+            }
+        }
+        *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = v;
+    }
+}
+__device__ __forceinline__ void stage_tile(uint8_t* smem, int stage_bytes, uint32_t lane_base, int set, int row, bool gdn,
+                                           int fuse, const float* __restrict__ bias, const float* __restrict__ beta)
+{
+    uint32_t ra[32], na[32], rb[32], nb[32];
+    // chunk q = 2 h + cc covers columns set * 64 + cc * 32 .. + 32 of half h
+    tmem_ld32_nowait(lane_base + kCol3Acc0 + set * 64, ra);
+    if (gdn) tmem_ld32_nowait(lane_base + kCol3Nrm0 + set * 64, na);
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int h = q >> 1, c0 = set * 64 + (q & 1) * 32;
+        tmem_ld_wait();
+        uint32_t* cur_r = (q & 1) ? rb : ra;
+        uint32_t* cur_n = (q & 1) ? nb : na;
+        if (q < 3) {
+            const int h2 = (q + 1) >> 1, c2 = set * 64 + ((q + 1) & 1) * 32;
+            tmem_ld32_nowait(lane_base + (h2 ? kCol3Acc1 : kCol3Acc0) + c2, (q & 1) ? ra : rb);
+            if (gdn) tmem_ld32_nowait(lane_base + (h2 ? kCol3Nrm1 : kCol3Nrm0) + c2, (q & 1) ? na : nb);
+        }
+        stage_chunk(smem + h * stage_bytes + (c0 / 32) * kTileBytes + row * 128, row, c0, cur_r, cur_n, gdn, fuse, bias, beta);
+    }
+}
+
 __global__ void __launch_bounds__(kUmmaThreads3, 1)
 gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
@@ -969,40 +1134,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
         // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (stage h of the ring,
         // four swizzled [128 x 32] sub-tiles) -> coalesced 512-byte rows.
-        #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            uint8_t* stage = smem + h * kStageBytes3;
-            #pragma unroll 1
-            for (int cc = 0; cc < 2; cc++) {
-                const int c0 = set * 64 + cc * 32;
-                tmem_ld32_nowait(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                if (n_gdn) tmem_ld32_nowait(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
-                tmem_ld_wait();
-                uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
-                #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-                    if (p.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
-                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                    }
-                    if (n_gdn) {
-                        // x * rsqrt(norm + beta) (GDN) or x * (n * rsqrt(n)) (IGDN): the 2-ulp MUFU forms; their error
-                        // (2^-22) is below that of the 3xTF32 contraction that produced x.
-                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * c));
-                        const float n0 = __uint_as_float(hi[4 * c]) + be.x, n1 = __uint_as_float(hi[4 * c + 1]) + be.y;
-                        const float n2 = __uint_as_float(hi[4 * c + 2]) + be.z, n3 = __uint_as_float(hi[4 * c + 3]) + be.w;
-                        if (p.fuse == 1) {
-                            v.x *= rsqrtf(n0); v.y *= rsqrtf(n1); v.z *= rsqrtf(n2); v.w *= rsqrtf(n3);
-                        } else {
-                            v.x *= n0 * rsqrtf(n0); v.y *= n1 * rsqrtf(n1); v.z *= n2 * rsqrtf(n2); v.w *= n3 * rsqrtf(n3);
-                        }
-                    }
-                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = v;
-                }
-            }
-        }
+        stage_tile(smem, kStageBytes3, lane_base, set, row, n_gdn != 0, p.fuse, p.bias, p.beta);
         named_bar_sync(1, 256);     // both sets finished staging
         if (stamp && threadIdx.x == 64) stamp[6] = clock64();
         // Coalesced stores: warp wq writes rows wq, wq + 8, ... of each half, one 512-byte pixel per instruction;
@@ -1119,10 +1251,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* u_full = bars + 8;           // [2] union box landed
     uint64_t* split = bars + 12;           // [2] TMEM A slot written (128 arrivals: one conversion set)
     uint64_t* acc_full = bars + 16;
-    uint64_t* g_full = bars + 17;          // [3] fused GDN ring
-    uint64_t* g_split = bars + 20;
-    uint64_t* g_empty = bars + 23;
-    uint64_t* nrm_full = bars + 26;
+    uint64_t* nrm_full = bars + 17;
+    const GdnTail tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[2] */, bars + 24 /* x_free[2] */, acc_full, nrm_full};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1137,7 +1267,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&u_full[s], 1); mbar_init(&split[s], 4); }     // one arrival per conversion warp
-        for (int s = 0; s < 3; s++) { mbar_init(&g_full[s], 1); mbar_init(&g_split[s], 4); mbar_init(&g_empty[s], 1); }
+        gdn_tail_init(tail);
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1196,19 +1326,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 tma_load_3d(st, &map_b_hi, &b_full[s], kc * kChunkK, 0, tap.w_tap);
                 if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &b_full[s], kc * kChunkK, 0, tap.w_tap);
             }
-            if (ok && n_gdn) {
-                // the GDN stages alias the main-loop buffers: wait until every main MMA has completed
-                ok = mbar_wait(acc_full, 0, p.error_flag, 0);
-                for (int j = 0; j < n_gdn && ok; j++) {
-                    const int s = j % 3;
-                    ok = mbar_wait(&g_empty[s], ((uint32_t)(j / 3) & 1u) ^ 1u, p.error_flag, 0);
-                    if (!ok) break;
-                    uint8_t* st = smem + s * kGdnStageBytes4;
-                    mbar_expect_tx(&g_full[s], 2 * kTileBytes);
-                    tma_load_3d(st + 2 * kTileBytes, &map_g_hi, &g_full[s], (j & 3) * kChunkK, 0, 0);
-                    tma_load_3d(st + 3 * kTileBytes, &map_g_lo, &g_full[s], (j & 3) * kChunkK, 0, 0);
-                }
-            }
+            if (ok && n_gdn) gdn_tail_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
@@ -1243,29 +1361,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 }
                 __syncwarp();
             }
-            for (int j = 0; j < n_gdn && ok; j++) {
-                // fused GDN: NRM_h += (x^2)_hi g_hi + (x^2)_lo g_hi + (x^2)_hi g_lo, operands in shared memory
-                const int s = j % 3, h = j >> 2, kc = j & 3;
-                ok = mbar_wait(&g_split[s], (uint32_t)(j / 3) & 1u, p.error_flag, 1);
-                ok = __all_sync(0xFFFFFFFFu, ok);
-                if (!ok) break;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(smem + s * kGdnStageBytes4);
-                    const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
-                    #pragma unroll
-                    for (int k = 0; k < kChunkK / 8; k++) {
-                        const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
-                        const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
-                        umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
-                        umma_tf32(d, x_lo, g_hi, 1u);
-                        umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
-                    }
-                    umma_commit(&g_empty[s]);
-                    if (j == n_gdn - 1) umma_commit(nrm_full);
-                }
-                __syncwarp();
-            }
+            if (ok && n_gdn) gdn_tail_mma(tail, p.error_flag);
         }
     } else {
         // ===== warps 2..9: two conversion / epilogue sets; set k owns TMEM A slot k and the iterations of parity k
@@ -1321,45 +1417,9 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[set]);      // 4 arrivals instead of 128: the arrive chain is on the critical path
         }
-        for (int j = set; j < n_gdn && ok; j += 2) {
-            const int s = j % 3;
-            uint8_t* st = smem + s * kGdnStageBytes4;
-            if (j < 2) {      // first GDN chunk of this set: the accumulators are final (and the main buffers free)
-                ok = mbar_wait(acc_full, 0, p.error_flag, 3);
-                if (!ok) break;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-            }
-            // the x^2 operands go to the A part of the stage: wait until the MMAs of its previous use are done
-            ok = mbar_wait(&g_empty[s], ((uint32_t)(j / 3) & 1u) ^ 1u, p.error_flag, 7);
-            if (!ok) break;
-            const int h = j >> 2, c0 = (j & 3) * kChunkK;
-            tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
-            uint8_t* rowp = st + row * 128;
-            #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                       __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-                if (p.bias) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
-                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                }
-                x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
-                float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
-                xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
-                *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            // the MMA also needs gamma: it waits for g_split only, so this set vouches for the TMA data too
-            ok = mbar_wait(&g_full[s], (uint32_t)(j / 3) & 1u, p.error_flag, 2);
-            if (!ok) break;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&g_split[s]);
+        if (ok && n_gdn) {
+            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
+            ok = gdn_tail_convert(tail, set, row, lane, lane_base, p.bias, p.error_flag);
         }
         if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1367,38 +1427,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
 
         // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (four swizzled [128 x 32]
         // sub-tiles per half) -> coalesced 512-byte rows.
-        #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            uint8_t* stage = smem + h * kGdnStageBytes4;
-            #pragma unroll 1
-            for (int cc = 0; cc < 2; cc++) {
-                const int c0 = set * 64 + cc * 32;
-                tmem_ld32_nowait(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                if (n_gdn) tmem_ld32_nowait(lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + c0, hi);
-                tmem_ld_wait();
-                uint8_t* sub = stage + (c0 / 32) * kTileBytes + row * 128;
-                #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-                    if (p.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
-                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                    }
-                    if (n_gdn) {
-                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4 * c));
-                        const float n0 = __uint_as_float(hi[4 * c]) + be.x, n1 = __uint_as_float(hi[4 * c + 1]) + be.y;
-                        const float n2 = __uint_as_float(hi[4 * c + 2]) + be.z, n3 = __uint_as_float(hi[4 * c + 3]) + be.w;
-                        if (p.fuse == 1) {
-                            v.x *= rsqrtf(n0); v.y *= rsqrtf(n1); v.z *= rsqrtf(n2); v.w *= rsqrtf(n3);
-                        } else {
-                            v.x *= n0 * rsqrtf(n0); v.y *= n1 * rsqrtf(n1); v.z *= n2 * rsqrtf(n2); v.w *= n3 * rsqrtf(n3);
-                        }
-                    }
-                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = v;
-                }
-            }
-        }
+        stage_tile(smem, kGdnStageBytes4, lane_base, set, row, n_gdn != 0, p.fuse, p.bias, p.beta);
         named_bar_sync(1, 256);     // both sets finished staging
         if (stamp && threadIdx.x == 64) stamp[6] = clock64();
         const int wq = warp - 2;
