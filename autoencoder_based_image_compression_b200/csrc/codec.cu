@@ -44,6 +44,16 @@ struct eae_codec {
     std::vector<double> table_host;    // the table the device copies were made from
     std::vector<float> delta_host, mean_host;
     uint64_t last_idx_elems = 0;
+    // pinned, device-visible result block of the _host entry points: one kernel writes it, one synchronisation reads it
+    struct HostMailbox* mailbox = nullptr;
+};
+
+struct HostMailbox {
+    uint64_t total;
+    uint32_t flag[2];       // [0] bit flags (int16 overflow), [1] first coder error
+    uint32_t umma_err;      // time-out mask of the tensor path (cleared on read)
+    uint32_t pad;
+    eae_batch_stats_t stats;
 };
 
 namespace {
@@ -428,6 +438,85 @@ __global__ void batch_stats_kernel(const uint32_t* __restrict__ bac_bits, const 
     if (err[s]) atomicCAS(flag + 1, 0u, err[s]);   // first stream error wins
 }
 
+// Everything a _host entry point needs to know about the batch, written straight into pinned host memory.
+__global__ void mailbox_kernel(HostMailbox* __restrict__ mb, const uint64_t* __restrict__ total,
+                               const uint32_t* __restrict__ flag, const eae_batch_stats_t* __restrict__ stats,
+                               uint32_t* __restrict__ umma_flag)
+{
+    if (threadIdx.x == 0) {
+        mb->total = total ? *total : 0ull;
+        mb->flag[0] = flag[0];
+        mb->flag[1] = flag[1];
+        mb->umma_err = umma_flag ? atomicExch(umma_flag, 0u) : 0u;
+    }
+    if (stats) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stats);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&mb->stats);
+        for (uint32_t i = threadIdx.x; i < sizeof(eae_batch_stats_t) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+}
+
+// dst[0 .. *nbytes) = src[0 .. *nbytes), 16 bytes per thread: the container goes to pinned host memory in wide,
+// coalesced writes without the host having to learn its size first (both buffers are 16-byte aligned).
+__global__ void copy_prefix_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                   const uint64_t* __restrict__ nbytes, uint64_t cap)
+{
+    const uint64_t n = *nbytes < cap ? *nbytes : cap;
+    const uint64_t n16 = (n + 15) / 16;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+// flag[1] = error code of the lowest-numbered stream with an error (0 if none), as the host loop used to find it.
+__global__ void first_error_kernel(const uint32_t* __restrict__ err, uint32_t n_streams, uint32_t* __restrict__ key)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams && err[s]) atomicMin(key, (s << 8) | (err[s] & 0xFFu));
+}
+__global__ void first_error_finish_kernel(uint32_t* key, uint32_t* flag1)
+{
+    *flag1 = *key == 0xFFFFFFFFu ? 0u : (*key & 0xFFu);
+}
+
+int ensure_mailbox(eae_codec* c)
+{
+    if (c->mailbox) return 0;
+    void* p = nullptr;
+    EAE_CUDA_OK(cudaHostAlloc(&p, sizeof(HostMailbox), cudaHostAllocPortable | cudaHostAllocMapped));
+    c->mailbox = reinterpret_cast<HostMailbox*>(p);
+    return 0;
+}
+
+int post_mailbox(eae_codec* c, const uint64_t* total_dev, const eae_batch_stats_t* stats_dev, cudaStream_t st)
+{
+    EAE_TRY(ensure_mailbox(c));
+    void* mb_dev = nullptr;
+    EAE_CUDA_OK(cudaHostGetDevicePointer(&mb_dev, c->mailbox, 0));
+    mailbox_kernel<<<1, 64, 0, st>>>(reinterpret_cast<HostMailbox*>(mb_dev), total_dev, c->flag.as<uint32_t>(), stats_dev,
+                                     c->math != EAE_MATH_FP32_SIMT ? umma_error_flag_dev() : nullptr);
+    EAE_LAUNCH_OK();
+    return 0;
+}
+
+int check_mailbox(const eae_codec* c, const char* what)
+{
+    const HostMailbox& mb = *c->mailbox;
+    if (mb.umma_err) { set_error("tcgen05 GEMM pipeline timed out (role mask 0x%x)", mb.umma_err); return EAE_ERR_CUDA; }
+    if (mb.flag[0] & 1u) { set_error("The rounded array elements cannot be represented as 16-bit signed integers."); return EAE_ERR_INT16_RANGE; }
+    if (mb.flag[1]) { set_error("Error of type %u during the %s.", mb.flag[1], what); return (int)mb.flag[1]; }
+    return 0;
+}
+
+// Device-visible alias of a host buffer if it is pinned / registered, else NULL.
+uint8_t* device_alias_of_pinned(const void* host)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+    return reinterpret_cast<uint8_t*>(attr.devicePointer);
+}
+
 int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* img_dev, uint32_t n,
                       uint32_t h, uint32_t w, uint8_t* container_dev, uint64_t cap, uint64_t* total_dev,
                       eae_batch_stats_t* stats_dev, cudaStream_t st)
@@ -636,6 +725,7 @@ extern "C" int eae_codec_destroy(eae_codec_t* c)
 {
     if (!c) return 0;
     cudaSetDevice(c->device);
+    if (c->mailbox) cudaFreeHost(c->mailbox);
     delete c;
     return 0;
 }
@@ -792,30 +882,34 @@ extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nin = (size_t)n * h * w;
     if (c->img_u8.bytes < nin) EAE_TRY(c->img_u8.alloc(nin));
-    // Device-side container: sized by the bytes actually produced is unknown before coding, so the
-    // staging buffer is sized by the caller's capacity (bounded by the worst case).
+    // The size of the container is only known after coding. It is assembled in device memory (sized by the caller's
+    // capacity, bounded by the worst case); when the caller's buffer is pinned host memory a kernel that reads the
+    // size on the device copies it there in wide writes (one synchronisation per call), otherwise the host copies
+    // it once it knows the size.
     uint64_t bound = eae_container_bound(n, h, w, prm ? prm->truncated_unary_length : 1);
     uint64_t dcap = cap < bound ? cap : bound;
-    if (c->rec_u8.bytes < dcap) EAE_TRY(c->rec_u8.alloc(dcap));
+    uint8_t* direct = device_alias_of_pinned(container);
+    if (direct && ((reinterpret_cast<uintptr_t>(direct) & 15u) || (cap & 15u))) direct = nullptr;     // needs 16-byte granularity
+    if (c->rec_u8.bytes < dcap + 16) EAE_TRY(c->rec_u8.alloc(dcap + 16));
     EAE_CUDA_OK(cudaMemcpyAsync(c->img_u8.p, img, nin, cudaMemcpyHostToDevice, st));
     if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
     EAE_TRY(compress_dev_impl(c, prm, c->img_u8.as<uint8_t>(), n, h, w, c->rec_u8.as<uint8_t>(), dcap,
                               c->total_bytes.as<uint64_t>(), nullptr, st));
-    uint64_t total = 0;
-    uint32_t flag[2] = {0, 0};
-    eae_batch_stats_t hs;
-    EAE_CUDA_OK(cudaMemcpyAsync(&total, c->total_bytes.p, 8, cudaMemcpyDeviceToHost, st));
-    EAE_CUDA_OK(cudaMemcpyAsync(flag, c->flag.p, 8, cudaMemcpyDeviceToHost, st));
-    EAE_CUDA_OK(cudaMemcpyAsync(&hs, c->stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+    if (direct) {
+        copy_prefix_kernel<<<148, 256, 0, st>>>(direct, c->rec_u8.as<uint8_t>(), c->total_bytes.as<uint64_t>(), dcap);
+        EAE_LAUNCH_OK();
+    }
+    EAE_TRY(post_mailbox(c, c->total_bytes.as<uint64_t>(), c->stats.as<eae_batch_stats_t>(), st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
-    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
-    if (flag[0] & 1u) { set_error("The rounded array elements cannot be represented as 16-bit signed integers."); return EAE_ERR_INT16_RANGE; }
-    if (flag[1]) { set_error("Error of type %u during the encoding.", flag[1]); return (int)flag[1]; }
+    EAE_TRY(check_mailbox(c, "encoding"));
+    const uint64_t total = c->mailbox->total;
     if (total > dcap) { set_error("container needs %llu bytes, capacity is %llu", (unsigned long long)total, (unsigned long long)cap); return EAE_ERR_ARGUMENT; }
-    EAE_CUDA_OK(cudaMemcpyAsync(container, c->rec_u8.p, total, cudaMemcpyDeviceToHost, st));
-    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    if (!direct) {
+        EAE_CUDA_OK(cudaMemcpyAsync(container, c->rec_u8.p, total, cudaMemcpyDeviceToHost, st));
+        EAE_CUDA_OK(cudaStreamSynchronize(st));
+    }
     *out_bytes = total;
-    if (stats) *stats = hs;
+    if (stats) *stats = c->mailbox->stats;
     return 0;
 }
 
@@ -851,13 +945,17 @@ extern "C" int eae_decompress_host(eae_codec_t* c, const eae_coding_params_t* pr
     if (c->img_u8.bytes < nout) EAE_TRY(c->img_u8.alloc(nout));
     EAE_CUDA_OK(cudaMemcpyAsync(c->rec_u8.p, container, nbytes, cudaMemcpyHostToDevice, st));
     EAE_TRY(decompress_dev_impl(c, prm, c->rec_u8.as<uint8_t>(), n, h, w, c->img_u8.as<uint8_t>(), st));
-    std::vector<uint32_t> herr(n_streams);
-    EAE_CUDA_OK(cudaMemcpyAsync(herr.data(), c->err.p, n_streams * 4, cudaMemcpyDeviceToHost, st));
+    // error of the lowest-numbered failing stream -> flag[1] -> mailbox; the reconstruction rides the same stream
+    EAE_CUDA_OK(cudaMemsetAsync(c->flag.as<uint32_t>() + 1, 0xFF, 4, st));
+    first_error_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(c->err.as<uint32_t>(), (uint32_t)n_streams,
+                                                                    c->flag.as<uint32_t>() + 1);
+    EAE_LAUNCH_OK();
+    first_error_finish_kernel<<<1, 1, 0, st>>>(c->flag.as<uint32_t>() + 1, c->flag.as<uint32_t>() + 1);
+    EAE_LAUNCH_OK();
+    EAE_TRY(post_mailbox(c, nullptr, nullptr, st));
     EAE_CUDA_OK(cudaMemcpyAsync(rec, c->img_u8.p, nout, cudaMemcpyDeviceToHost, st));
     EAE_CUDA_OK(cudaStreamSynchronize(st));
-    if (c->math != EAE_MATH_FP32_SIMT) EAE_TRY(umma_check_error(st));
-    for (uint64_t s = 0; s < n_streams; s++)
-        if (herr[s]) { set_error("Error of type %u during the decoding.", herr[s]); return (int)herr[s]; }
+    EAE_TRY(check_mailbox(c, "decoding"));
     return 0;
 }
 

@@ -1539,6 +1539,8 @@ int umma_available()
     return 0;
 }
 
+uint32_t* umma_error_flag_dev() { return g_error_flag; }
+
 int umma_check_error(cudaStream_t st)
 {
     if (!g_error_flag) return 0;

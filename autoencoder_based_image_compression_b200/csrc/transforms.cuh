@@ -27,6 +27,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
 int umma_version();
 // Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
 int umma_check_error(cudaStream_t st);
+// The device word behind umma_check_error (NULL before the first tensor-path launch); kernels may read and clear it.
+uint32_t* umma_error_flag_dev();
 // 0 if the tcgen05 path can run on the current device (sm_100), else an error code with message.
 int umma_available();
 
