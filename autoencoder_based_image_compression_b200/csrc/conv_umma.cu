@@ -732,110 +732,97 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-// ---- fused GDN / IGDN tail shared by versions 3 and 4 --------------------------------------------------------
+// ---- fused GDN / IGDN tail (version 4) ---------------------------------------------------------------------
 // NRM_h = (x_h^2) gamma for both 128-row halves h, x = accumulator + bias, as 8 steps j = 4 h + kc over the four
-// 32-channel chunks of x^2. gamma (hi | lo, 4 x 32 KB) is loaded ONCE and stays resident; (x^2)_hi / (x^2)_lo of a
-// step go to one of two 32 KB buffers (conversion set k owns buffer k, as it owns TMEM slot k in the main loop),
-// all in the 192 KB that the main loop has just released:
-//   area + 0 / + 32K : X[0] / X[1] = { (x^2)_hi 16K | (x^2)_lo 16K }, canonical K-major SWIZZLE_128B tiles
-//   area + 64K + kc * 32K : gamma chunk kc = { hi 16K | lo 16K }
+// 32-channel chunks of x^2, in the shared memory the main loop has just released:
+//   stage s = j & 1 at area + s * 64K = { (x^2)_hi 16K | (x^2)_lo 16K | gamma_hi chunk 16K | gamma_lo chunk 16K }
+//     (conversion set k owns stage k, as it owns TMEM slot k in the main loop; the TMA producer refills its gamma part)
+//   area + 128K .. 192K : output staging of half 0;  area + 0 .. 64K : output staging of half 1 (after the last MMA)
+// The halves are pipelined: once the four steps of half 0 are done (nrm0_full) the conversion warps normalise,
+// stage and STORE half 0 between their two remaining conversions, while the tensor pipe works on half 1. Only
+// half 1's read-out and store remain after the last MMA.
 struct GdnTail {
     uint8_t* area;
-    uint64_t* g_full;      // [4] gamma chunk kc landed (single use)
-    uint64_t* x_ready;     // [2] x^2 buffer written (4 arrivals: one per conversion warp of the set)
-    uint64_t* x_free;      // [2] the MMAs that read the buffer completed
+    uint64_t* g_full;      // [2] gamma chunk of the step landed in stage s
+    uint64_t* x_ready;     // [2] x^2 of the step written to stage s (4 arrivals: one per conversion warp of the set)
+    uint64_t* x_free;      // [2] the MMAs that read stage s completed
     uint64_t* acc_full;
+    uint64_t* nrm0_full;
     uint64_t* nrm_full;
 };
 __device__ __forceinline__ void gdn_tail_init(const GdnTail& t)
 {
-    for (int s = 0; s < 4; s++) mbar_init(&t.g_full[s], 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&t.g_full[s], 1); mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
+    mbar_init(t.nrm0_full, 1);
 }
 // TMA producer thread, after its last main-loop load.
 __device__ __forceinline__ void gdn_tail_producer(const GdnTail& t, const CUtensorMap* map_g_hi, const CUtensorMap* map_g_lo,
                                                   uint32_t* error_flag)
 {
-    // gamma lands on the buffers of the main loop: wait until every main MMA has completed
+    // the stages alias the buffers of the main loop: wait until every main MMA has completed
     if (!mbar_wait(t.acc_full, 0, error_flag, 0)) return;
-    for (int kc = 0; kc < 4; kc++) {
-        uint8_t* g = t.area + 4 * kTileBytes + kc * 2 * kTileBytes;
-        mbar_expect_tx(&t.g_full[kc], 2 * kTileBytes);
-        tma_load_3d(g, map_g_hi, &t.g_full[kc], kc * kChunkK, 0, 0);
-        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[kc], kc * kChunkK, 0, 0);
+    for (int j = 0; j < 8; j++) {
+        const int s = j & 1;
+        if (j >= 2 && !mbar_wait(&t.x_free[s], (uint32_t)((j >> 1) - 1) & 1u, error_flag, 0)) return;
+        uint8_t* g = t.area + s * 4 * kTileBytes + 2 * kTileBytes;
+        mbar_expect_tx(&t.g_full[s], 2 * kTileBytes);
+        tma_load_3d(g, map_g_hi, &t.g_full[s], (j & 3) * kChunkK, 0, 0);
+        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[s], (j & 3) * kChunkK, 0, 0);
     }
 }
 // MMA warp (all lanes; one elected lane issues).
 __device__ __forceinline__ void gdn_tail_mma(const GdnTail& t, uint32_t* error_flag)
 {
     for (int j = 0; j < 8; j++) {
-        const int h = j >> 2, kc = j & 3, buf = j & 1;
-        bool ok = mbar_wait(&t.x_ready[buf], (uint32_t)(j >> 1) & 1u, error_flag, 1);
-        if (ok) ok = mbar_wait(&t.g_full[kc], 0, error_flag, 1);
+        const int h = j >> 2, kc = j & 3, s = j & 1;
+        bool ok = mbar_wait(&t.x_ready[s], (uint32_t)(j >> 1) & 1u, error_flag, 1);
+        if (ok) ok = mbar_wait(&t.g_full[s], (uint32_t)(j >> 1) & 1u, error_flag, 1);
         if (!__all_sync(0xFFFFFFFFu, ok)) return;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-            const uint32_t x = smem_u32(t.area + buf * 2 * kTileBytes);
-            const uint32_t g = smem_u32(t.area + 4 * kTileBytes + kc * 2 * kTileBytes);
+            const uint32_t st = smem_u32(t.area + s * 4 * kTileBytes);
             const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
             #pragma unroll
             for (int k = 0; k < kChunkK / 8; k++) {
-                const uint64_t x_hi = make_desc(x + k * 32), x_lo = make_desc(x + kTileBytes + k * 32);
-                const uint64_t g_hi = make_desc(g + k * 32);
+                const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
+                const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
                 umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
                 umma_tf32(d, x_lo, g_hi, 1u);
-                umma_tf32(d, x_hi, make_desc(g + kTileBytes + k * 32), 1u);
+                umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
             }
-            umma_commit(&t.x_free[buf]);
+            umma_commit(&t.x_free[s]);
+            if (j == 3) umma_commit(t.nrm0_full);
             if (j == 7) umma_commit(t.nrm_full);
         }
         __syncwarp();
     }
 }
-// Conversion warps of set `set` (thread = accumulator row): steps j = set, set + 2, ...
-__device__ __forceinline__ bool gdn_tail_convert(const GdnTail& t, int set, int row, int lane, uint32_t lane_base,
-                                                 const float* __restrict__ bias, uint32_t* error_flag)
+// One conversion step of set `set`: x = acc + bias from the chunk already requested into r, x^2 split into the stage.
+__device__ __forceinline__ void gdn_tail_square(const GdnTail& t, int set, int row, int lane, int c0, const uint32_t* r,
+                                                const float* __restrict__ bias)
 {
-    if (!mbar_wait(t.acc_full, 0, error_flag, 3)) return false;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint8_t* rowp = t.area + set * 2 * kTileBytes + row * 128;
-    uint32_t ra[32], rb[32];
-    tmem_ld32_nowait(lane_base + kCol3Acc0 + set * kChunkK, ra);     // step j = set: half 0, chunk `set`
+    uint8_t* rowp = t.area + set * 4 * kTileBytes + row * 128;
     #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
-        tmem_ld_wait();
-        uint32_t* r = (i & 1) ? rb : ra;
-        if (i < 3) {      // the accumulator chunk of this set's next step is read while this one is squared
-            const int j2 = j + 2;
-            tmem_ld32_nowait(lane_base + ((j2 >> 2) ? kCol3Acc1 : kCol3Acc0) + (j2 & 3) * kChunkK, (i & 1) ? ra : rb);
+    for (int c = 0; c < 8; c++) {
+        float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                               __uint_as_float(r[4 * c + 3]));
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
+            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
         }
-        if (i >= 1) {     // the MMAs of step j - 2 read this buffer
-            if (!mbar_wait(&t.x_free[set], (uint32_t)(i - 1) & 1u, error_flag, 7)) return false;
-        }
-        #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
-                                   __uint_as_float(r[4 * c + 3]));
-            if (bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
-                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-            }
-            x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
-            float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
-            xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-            xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-            xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-            xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
-            *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t.x_ready[set]);
+        x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
+        float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
+        xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
+        *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
     }
-    return true;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t.x_ready[set]);
 }
 
 // Epilogue staging shared by versions 3 and 4: this thread's row, this set's 64 channels of both halves:
@@ -894,6 +881,51 @@ __device__ __forceinline__ void stage_tile(uint8_t* smem, int stage_bytes, uint3
             if (gdn) tmem_ld32_nowait(lane_base + (h2 ? kCol3Nrm1 : kCol3Nrm0) + c2, (q & 1) ? na : nb);
         }
         stage_chunk(smem + h * stage_bytes + (c0 / 32) * kTileBytes + row * 128, row, c0, cur_r, cur_n, gdn, fuse, bias, beta);
+    }
+}
+
+// This set's 64 channels of ONE half -> `stage` (64 KB, four swizzled [128 x 32] sub-tiles), and the coalesced store
+// of a staged half (version 4 geometry: 16 x 16 positions per tile, half h = rows 8 h .. 8 h + 7).
+__device__ __forceinline__ void stage_half(uint8_t* stage, int h, uint32_t lane_base, int set, int row, bool gdn, int fuse,
+                                           const float* __restrict__ bias, const float* __restrict__ beta)
+{
+    uint32_t ra[32], na[32], rb[32], nb[32];
+    const uint32_t acc = lane_base + (h ? kCol3Acc1 : kCol3Acc0) + set * 64, nrm = lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + set * 64;
+    tmem_ld32_nowait(acc, ra);
+    if (gdn) tmem_ld32_nowait(nrm, na);
+    tmem_ld_wait();
+    tmem_ld32_nowait(acc + 32, rb);
+    if (gdn) tmem_ld32_nowait(nrm + 32, nb);
+    stage_chunk(stage + (set * 2) * kTileBytes + row * 128, row, set * 64, ra, na, gdn, fuse, bias, beta);
+    tmem_ld_wait();
+    stage_chunk(stage + (set * 2 + 1) * kTileBytes + row * 128, row, set * 64 + 32, rb, nb, gdn, fuse, bias, beta);
+}
+struct OutGeom4 {
+    float* out;
+    int img, a0, b0, Hg, Wg, Hout, Wout, out_mul, out_r, out_s, out_split;
+};
+__device__ __forceinline__ void store_half4(const OutGeom4& g, const uint8_t* stage, int h, int wq, int lane, bool ok)
+{
+    #pragma unroll 1
+    for (int j0 = 0; j0 < kTileM / 8; j0 += 4) {
+        float4 v[4];
+        float* dst[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int rr = wq + 8 * (j0 + j);
+            const int a = g.a0 + h * 8 + (rr >> 4), b = g.b0 + (rr & 15);
+            const int oy = a * g.out_mul + g.out_r, ox = b * g.out_mul + g.out_s;
+            size_t opix;
+            if (g.out_split)
+                opix = (((size_t)g.img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (g.Hout / 2) + (oy >> 1)) * (g.Wout / 2) + (ox >> 1);
+            else
+                opix = ((size_t)g.img * g.Hout + oy) * g.Wout + ox;
+            dst[j] = (ok && a < g.Hg && b < g.Wg) ? g.out + opix * kCout + lane * 4 : nullptr;
+            v[j] = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+        }
+        #pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (dst[j]) *reinterpret_cast<float4*>(dst[j]) = v[j];
     }
 }
 
@@ -1252,7 +1284,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* split = bars + 12;           // [2] TMEM A slot written (128 arrivals: one conversion set)
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
-    const GdnTail tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[2] */, bars + 24 /* x_free[2] */, acc_full, nrm_full};
+    const GdnTail tail{smem, bars + 18 /* g_full[2] */, bars + 20 /* x_ready[2] */, bars + 22 /* x_free[2] */, acc_full,
+                       bars + 24 /* nrm0_full */, nrm_full};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1417,45 +1450,50 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[set]);      // 4 arrivals instead of 128: the arrive chain is on the critical path
         }
-        if (ok && n_gdn) {
-            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-            ok = gdn_tail_convert(tail, set, row, lane, lane_base, p.bias, p.error_flag);
-        }
-        if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (stamp && threadIdx.x == 64) stamp[5] = clock64();
-
-        // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (four swizzled [128 x 32]
-        // sub-tiles per half) -> coalesced 512-byte rows.
-        stage_tile(smem, kGdnStageBytes4, lane_base, set, row, n_gdn != 0, p.fuse, p.bias, p.beta);
-        named_bar_sync(1, 256);     // both sets finished staging
-        if (stamp && threadIdx.x == 64) stamp[6] = clock64();
         const int wq = warp - 2;
-        #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const uint8_t* stage = smem + h * kGdnStageBytes4;
-            #pragma unroll 1
-            for (int j0 = 0; j0 < kTileM / 8; j0 += 4) {
-                float4 v[4];
-                float* dst[4];
-                #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int rr = wq + 8 * (j0 + j);
-                    const int a = a0 + h * 8 + (rr >> 4), b = b0 + (rr & 15);
-                    const int oy = a * p.out_mul + p.out_r, ox = b * p.out_mul + p.out_s;
-                    size_t opix;
-                    if (p.out_split)
-                        opix = (((size_t)img * 4 + (size_t)((oy & 1) * 2 + (ox & 1))) * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1);
-                    else
-                        opix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
-                    dst[j] = (ok && a < p.Hg && b < p.Wg) ? p.out + opix * kCout + lane * 4 : nullptr;
-                    v[j] = *reinterpret_cast<const float4*>(stage + (lane >> 3) * kTileBytes + rr * 128 +
-                                                            (((lane & 7) ^ (rr & 7)) << 4));
+        const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
+        uint8_t* stage0 = smem + (n_gdn ? 2 : 0) * kGdnStageBytes4;     // half 0: above the two GDN stages when GDN is fused
+        uint8_t* stage1 = smem + (n_gdn ? 0 : 1) * kGdnStageBytes4;
+        if (ok && n_gdn) {
+            // ---- fused GDN / IGDN: this set converts steps j = set + 2 i; half 0 leaves while half 1 is contracted
+            ok = mbar_wait(acc_full, 0, p.error_flag, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
+            #pragma unroll
+            for (int i = 0; i < 4 && ok; i++) {
+                const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
+                tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                if (i >= 1) ok = mbar_wait(&tail.x_free[set], (uint32_t)(i - 1) & 1u, p.error_flag, 7);    // MMAs of step j - 2
+                tmem_ld_wait();
+                if (!ok) break;
+                gdn_tail_square(tail, set, row, lane, c0, r, p.bias);
+                if (i == 3) {
+                    // this set's conversions are done; the norm of half 0 has been complete since step 3: normalise,
+                    // stage and store half 0 while the tensor pipe contracts half 1
+                    ok = mbar_wait(tail.nrm0_full, 0, p.error_flag, 4);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (!ok) break;
+                    stage_half(stage0, 0, lane_base, set, row, true, p.fuse, p.bias, p.beta);
+                    named_bar_sync(1, 256);     // both sets staged half 0
+                    store_half4(geom, stage0, 0, wq, lane, ok);
                 }
-                #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (dst[j]) *reinterpret_cast<float4*>(dst[j]) = v[j];
             }
+            if (ok) ok = mbar_wait(nrm_full, 0, p.error_flag, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+            stage_half(stage1, 1, lane_base, set, row, true, p.fuse, p.bias, p.beta);
+            named_bar_sync(1, 256);
+            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+            store_half4(geom, stage1, 1, wq, lane, ok);
+        } else {
+            if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+            stage_tile(smem, kGdnStageBytes4, lane_base, set, row, false, 0, p.bias, p.beta);
+            named_bar_sync(1, 256);     // both sets finished staging
+            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+            store_half4(geom, stage0, 0, wq, lane, ok);
+            store_half4(geom, stage1, 1, wq, lane, ok);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
