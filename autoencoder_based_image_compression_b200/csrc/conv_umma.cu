@@ -945,7 +945,9 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* acc_full = bars + 3 * kStages3;
     uint64_t* nrm_full = bars + 3 * kStages3 + 1;
     uint64_t* img_full = bars + 3 * kStages3 + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages3 + 3);
+    const GdnTail tail{smem, bars + 12 /* g_full[2] */, bars + 14 /* x_ready[2] */, bars + 16 /* x_free[2] */, acc_full,
+                       bars + 18 /* nrm0_full */, nrm_full};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
@@ -965,6 +967,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
         mbar_init(img_full, 1);
+        gdn_tail_init(tail);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -986,7 +989,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
     // conv1: the A operand is an exact small integer (a pixel), so it has no low part
     const bool a_has_lo = p.exact_main && !p.conv1;
-    const int n_total = n_main + n_gdn;
+    const int n_total = n_main;                   // the fused GDN steps run in the shared tail (gdn_tail_*), not in this ring
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -1012,13 +1015,9 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                 a0 + p.half_da + tap.fy, tap.plane, img);
                     tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full[s], kc * kChunkK, 0, tap.w_tap);
                     if (p.exact_main) tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
-                } else {
-                    const int kc = (it - n_main) & 3;     // gamma chunk (each half re-loads it)
-                    mbar_expect_tx(&full[s], 2 * kTileBytes);
-                    tma_load_3d(st + 2 * kTileBytes, &map_g_hi, &full[s], kc * kChunkK, 0, 0);
-                    tma_load_3d(st + 3 * kTileBytes, &map_g_lo, &full[s], kc * kChunkK, 0, 0);
                 }
             }
+            if (n_gdn) gdn_tail_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (warp-uniform operands) =====
@@ -1043,25 +1042,13 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             if (p.exact_main) umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + 3 * kTileBytes + k * 32), 1u);
                         }
                     }
-                } else {
-                    // fused GDN: NRM_h += (x^2)_hi g_hi + (x^2)_lo g_hi + (x^2)_hi g_lo, operands in shared memory
-                    const int g = it - n_main, h = g >> 2, kc = g & 3;
-                    const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
-                    #pragma unroll
-                    for (int k = 0; k < kChunkK / 8; k++) {
-                        const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
-                        const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
-                        umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
-                        umma_tf32(d, x_lo, g_hi, 1u);
-                        umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
-                    }
                 }
                 umma_commit(&empty[s]);
                 if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
-                if (n_gdn && it == n_total - 1) umma_commit(nrm_full);
             }
             __syncwarp();
         }
+        if (n_gdn) gdn_tail_mma(tail, p.error_flag);
     } else {
         // ===== warps 2..9: two conversion / epilogue sets (set = iteration parity) =====
         const int quarter = warp & 3;
@@ -1128,45 +1115,51 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            } else {
-                if (it == n_main || it == n_main + 1) {
-                    ok = mbar_wait(acc_full, 0, p.error_flag, 3);
-                    if (!ok) break;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-                }
-                const int g = it - n_main, h = g >> 2, c0 = (g & 3) * kChunkK;
-                tmem_ld32(lane_base + (h ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                uint8_t* rowp = st + row * 128;
-                #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                           __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-                    if (p.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * c));
-                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                    }
-                    x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
-                    float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
-                    xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                    xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                    xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                    xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
-                    *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
             mbar_arrive(&split[s]);
         }
-        if (ok) ok = mbar_wait(n_gdn ? nrm_full : acc_full, 0, p.error_flag, 4);
+        if (n_gdn) {
+            // ---- fused GDN / IGDN (tile geometry 16 x 16, as in version 4): this set converts steps j = set + 2 i; half 0 is
+            // normalised, staged and stored while the tensor pipe contracts half 1
+            const int wq = warp - 2;
+            const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
+            uint8_t* stage0 = smem + 2 * kStageBytes3;
+            uint8_t* stage1 = smem;
+            if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
+            #pragma unroll
+            for (int i = 0; i < 4 && ok; i++) {
+                const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
+                tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
+                if (i >= 1) ok = mbar_wait(&tail.x_free[set], (uint32_t)(i - 1) & 1u, p.error_flag, 7);
+                tmem_ld_wait();
+                if (!ok) break;
+                gdn_tail_square(tail, set, row, lane, c0, r, p.bias);
+                if (i == 3) {
+                    ok = mbar_wait(tail.nrm0_full, 0, p.error_flag, 4);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (!ok) break;
+                    stage_half(stage0, 0, lane_base, set, row, true, p.fuse, p.bias, p.beta);
+                    named_bar_sync(1, 256);
+                    store_half4(geom, stage0, 0, wq, lane, ok);
+                }
+            }
+            if (ok) ok = mbar_wait(nrm_full, 0, p.error_flag, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+            stage_half(stage1, 1, lane_base, set, row, true, p.fuse, p.bias, p.beta);
+            named_bar_sync(1, 256);
+            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+            store_half4(geom, stage1, 1, wq, lane, ok);
+        } else {
+        if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (stamp && threadIdx.x == 64) stamp[5] = clock64();
 
         // ---- epilogue: this set's 64 channels of both halves -> shared-memory staging (stage h of the ring,
         // four swizzled [128 x 32] sub-tiles) -> coalesced 512-byte rows.
-        stage_tile(smem, kStageBytes3, lane_base, set, row, n_gdn != 0, p.fuse, p.bias, p.beta);
+        stage_tile(smem, kStageBytes3, lane_base, set, row, false, 0, p.bias, p.beta);
         named_bar_sync(1, 256);     // both sets finished staging
         if (stamp && threadIdx.x == 64) stamp[6] = clock64();
         // Coalesced stores: warp wq writes rows wq, wq + 8, ... of each half, one 512-byte pixel per instruction;
@@ -1213,6 +1206,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int j = 0; j < 4; j++)
                     if (dst[j]) *reinterpret_cast<float4*>(dst[j]) = v[j];
             }
+        }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1623,7 +1617,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     p.n_taps = plan.n_taps;
     p.kchunks = plan.Cin / kChunkK;
     // Position grids that are wide enough use 16 x 8 tiles; flat (1-row) grids use 128 x 1.
-    if (plan.Hg == 1) { p.tile_w = 128; p.tile_h = 1; } else { p.tile_w = 16; p.tile_h = 8; }
+    // (a fused GDN tail stores 16 x 16 tiles, so a one-row grid with fusion keeps the 2-D tiling)
+    if (plan.Hg == 1 && !plan.fuse) { p.tile_w = 128; p.tile_h = 1; } else { p.tile_w = 16; p.tile_h = 8; }
     p.tiles_x = (plan.Wg + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (plan.Hg + p.tile_h - 1) / p.tile_h;
     p.Hg = plan.Hg; p.Wg = plan.Wg;
@@ -1763,7 +1758,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;
         q.tile_w = p.tile_w; q.tile_h = p.tile_h;
         q.tile_w_log2 = p.tile_w == 128 ? 7 : 4;
-        if (plan.Hg == 1) { q.half_da = 0; q.half_db = p.tile_w; } else { q.half_da = p.tile_h; q.half_db = 0; }
+        if (p.tile_h == 1) { q.half_da = 0; q.half_db = p.tile_w; } else { q.half_da = p.tile_h; q.half_db = 0; }
         q.tiles_x = (plan.Wg + q.tile_w + q.half_db - 1) / (q.tile_w + q.half_db);
         q.tiles_y = (plan.Hg + q.tile_h + q.half_da - 1) / (q.tile_h + q.half_da);
         q.Hg = p.Hg; q.Wg = p.Wg;
@@ -1780,8 +1775,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.n_tiles = (int)grid3;
         CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo, map_img = map_b_hi;
         if (plan.fuse) {
-            if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias) {
-                set_error("gemm_umma: fused GDN needs gamma hi/lo, beta and a bias-mode contraction");
+            if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias || p.tile_h == 1) {
+                set_error("gemm_umma: fused GDN needs gamma hi/lo, beta, a bias-mode contraction and 2-D tiles");
                 return EAE_ERR_ARGUMENT;
             }
             const uint64_t gdims[3] = {kCout, kCout, 1};
