@@ -413,8 +413,8 @@ def run_gpu_arm(args):
               'fp32': {'gemm_conv': 0., 'gemm_tconv': 0., 'gemm_gdn': 0., 'gemm_thin': 0.}}[args.math]
     executed = sum(GFLOP_PER_IMAGE[k]*passes[k] for k in GFLOP_PER_IMAGE)*scale*n*args.steps/gemm_ms if gemm_ms > 0 else 0.
     # DRAM bytes per launch of this kernel from the committed ncu capture of this workload
-    # (profiles/r01_ncu_full_gemm_umma3_layers.md: 13 launches per step, 1805 MB per 24-image step).
-    traffic = 1804.9e6/13.*(n/24.)*scale if args.math != 'fp32' else None
+    # (profiles/r01_ncu_full_gemm_layers_final.md: 13 launches per step, 1810 MB per 24-image step).
+    traffic = 1810.1e6/13.*(n/24.)*scale if args.math != 'fp32' else None
     line['roofline'] = {
         'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
         'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',

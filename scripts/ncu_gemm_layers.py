@@ -1,0 +1,64 @@
+"""Per-layer table of the tap-list GEMM launches of one bench step from an ``ncu --set full`` capture.
+
+    ncu -i gpurun_out/prof_rXX_gemm.ncu-rep --page raw --csv > raw.csv
+    python scripts/ncu_gemm_layers.py raw.csv "title" > profiles/rXX_ncu_full_gemm_layers.md
+"""
+import csv
+import sys
+
+NAMES = ['conv1 k9 s4 (uint8 patches in-kernel) + GDN1', 'conv2 k5 s2 + GDN2', 'conv3 k5 s2 + GDN3', 'IGDN4 (standalone)',
+         'tconv1 phase (0,0), 4 taps + IGDN5', 'tconv1 phase (0,1), 6 taps + IGDN5', 'tconv1 phase (1,0), 6 taps + IGDN5',
+         'tconv1 phase (1,1), 9 taps + IGDN5', 'tconv2 phase (0,0), 4 taps + IGDN6', 'tconv2 phase (0,1), 6 taps + IGDN6',
+         'tconv2 phase (1,0), 6 taps + IGDN6', 'tconv2 phase (1,1), 9 taps + IGDN6',
+         'tconv3 k9 s4 (per-pixel tap matrix; col2im follows)']
+# algorithmic GFLOP per image and MMA passes actually issued
+ALG = [0.5096 + 0.8053, 5.0332 + 0.2013, 1.2583 + 0.0503, 0.0503] + [1.2583*t/25 + 0.2013/4 for t in (4, 6, 6, 9)] + \
+      [5.0332*t/25 + 0.8053/4 for t in (4, 6, 6, 9)] + [0.5096]
+EXE = [0.5096*2 + 0.8053*3, (5.0332 + 0.2013)*3, (1.2583 + 0.0503)*3, 0.0503*3] + \
+      [(1.2583*t/25 + 0.2013/4)*3 for t in (4, 6, 6, 9)] + [(5.0332*t/25 + 0.8053/4)*3 for t in (4, 6, 6, 9)] + [0.5096*3]
+
+
+def main():
+    rows = list(csv.reader(open(sys.argv[1])))
+    title = sys.argv[2] if len(sys.argv) > 2 else 'tap-list GEMM, every layer of one 24-image step'
+    images = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+    hdr = rows[0]
+
+    def col(name):
+        for (i, h) in enumerate(hdr):
+            if h == name or h.endswith('.' + name):
+                return i
+        return None
+
+    c = {k: col(k) for k in ['Kernel Name', 'launch__grid_size', 'gpu__time_duration.sum', 'dram__bytes_read.sum',
+                             'dram__bytes_write.sum', 'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
+                             'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'launch__registers_per_thread',
+                             'launch__shared_mem_per_block_dynamic']}
+    print('# ' + title + '\n')
+    print('Source: `ncu --set full --clock-control none --import-source on -k regex:gemm_umma -s 13 -c 13` around '
+          '`python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline` on one B200, read with `ncu -i ... --page raw --csv` '
+          '(`scripts/ncu_gemm_layers.py`). Durations under ncu are cold-cache and serialised (SM clock {} GHz in the capture); the '
+          'bench line is the timing. One launch = one layer (or one output phase of a transposed convolution) over {} images of '
+          '512 x 768.\n'.format(rows[2][c['sm__cycles_elapsed.avg.per_second']][:5], images))
+    print('| launch | kernel | grid | duration us | DRAM read MB | DRAM write MB | tensor sub-pipe active / (4 x SM cycles) | '
+          'algorithmic TFLOP/s | executed-MMA TFLOP/s |')
+    print('|---|---|---|---|---|---|---|---|---|')
+    (tt, tr, tw, ta, te) = (0., 0., 0., 0., 0.)
+    for (k, r) in enumerate(rows[2:2 + len(NAMES)]):
+        d = float(r[c['gpu__time_duration.sum']])
+        rd = float(r[c['dram__bytes_read.sum']])
+        wr = float(r[c['dram__bytes_write.sum']])
+        h = float(r[c['sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg']])
+        cy = float(r[c['sm__cycles_elapsed.avg']])
+        kern = 'v4' if 'umma4' in r[c['Kernel Name']] else 'v3'
+        print('| {} | {} | {} | {:.1f} | {:.1f} | {:.1f} | {:.1f} % | {:.0f} | {:.0f} |'.format(
+            NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, 100.*h/(4.*cy), ALG[k]*images/d*1e3, EXE[k]*images/d*1e3))
+        tt += d; tr += rd; tw += wr; ta += ALG[k]*images; te += EXE[k]*images
+    print('| **all 13 launches** | | | **{:.1f}** | **{:.1f}** | **{:.1f}** | | **{:.0f}** | **{:.0f}** |'.format(
+        tt, tr, tw, ta/tt*1e3, te/tt*1e3))
+    print()
+    print('DRAM traffic of the 13 launches: {:.0f} MB per step = {:.1f} MB per launch on average.'.format(tr + tw, (tr + tw)/13.))
+
+
+if __name__ == '__main__':
+    main()
