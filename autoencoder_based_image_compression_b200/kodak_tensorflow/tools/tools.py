@@ -114,6 +114,13 @@ def count_nb_deads(array_4d):
     return nb_deads.astype(numpy.int64)
 
 
+def float_to_str(float_in):
+    """tools.py:570-593: "." becomes "dot" for non-whole numbers, "-" becomes "minus" (used in result paths)."""
+    float_in = float(float_in)
+    str_in = str(int(float_in)) if float_in.is_integer() else str(float_in).replace('.', 'dot')
+    return str_in.replace('-', 'minus')
+
+
 def psnr_2d(reference_uint8, reconstruction_uint8):
     """tools.py:831-881: 10 log10(255^2 / mse) with the squared-error sum reduced on the GPU (exact
     integer), the division and logarithm in float64 as in the reference."""

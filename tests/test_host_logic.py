@@ -167,6 +167,8 @@ def test_drop_in_module_names_resolve(tmp_path):
     code = ("import sys; sys.path.insert(0, {root!r}); "
             "sys.path.insert(0, {root!r} + '/autoencoder_based_image_compression_b200/kodak_tensorflow'); "
             "import eae.batching, lossless.compression, lossless.interface_cython, lossless.stats, tools.tools as tls; "
+            "import reconstructing_eae_kodak; assert callable(reconstructing_eae_kodak.fix_gamma); "
+            "assert tls.float_to_str(0.5) == '0dot5' and tls.float_to_str(10000.) == '10000' and tls.float_to_str(-1.5) == 'minus1dot5'; "
             "from eae.graph.EntropyAutoencoder import EntropyAutoencoder; "
             "from eae.graph.IsolatedDecoder import IsolatedDecoder; "
             "import eae.graph.constants as csts; "
