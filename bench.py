@@ -88,23 +88,28 @@ def cpu_pipeline(images, weights, table, map_mean, cores, pool, which):
     rec = numpy.zeros(images.shape, dtype=numpy.uint8)
     bits = 0
     mean = map_mean.reshape((1, 1, 1, -1))
+    pending = []
     for i0 in range(0, images.shape[0], 4):          # reconstructing_eae_kodak.py:624 batch_size = 4
         x = images[i0:i0 + 4, :, :, None].astype(numpy.float32)
         y = transforms.encoder(x, weights, False)
         cq = glue.quantize_per_map(y - mean, numpy.ones(128, dtype=numpy.float32))
         idx = glue.cast_float_to_int16(cq)
         planar = [numpy.ascontiguousarray(idx[j].reshape(-1, 128).T) for j in range(idx.shape[0])]
-        bits += sum(pool.map(_cpu_code_one, [(p, table, which) for p in planar]))
+        # the coder of these images runs in the worker processes while the main process goes on with the transforms
+        pending.append(pool.map_async(_cpu_code_one, [(p, table, which) for p in planar]))
         rec[i0:i0 + 4] = glue.cast_bt601(transforms.decoder(cq + mean, weights, False))[..., 0]
+    bits = sum(sum(job.get()) for job in pending)
     return (time.perf_counter() - t0, bits, rec)
 
 
-def run_cpu_arm(args, steps, warmup):
+def run_cpu_arm(args, steps, warmup, sample_per_core=1):
     from autoencoder_based_image_compression_b200 import synthetic
     from autoencoder_based_image_compression_b200 import weights as wts
     from oracle import coder
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(4, min(cores, 16))
+    # images per step: a multiple of the core count (one image per worker process); the cpu_baseline leg of the GPU
+    # arm runs ONE step of 16 images per core (about 10 s of CPU work), the reference arm K steps of one image per core
+    sample = args.cpu_sample or max(4, min(cores, 32)*sample_per_core)
     which = 'ref' if coder.has_ref() else 'port'
     coder.build()
     (table, map_mean) = load_tables()
@@ -431,7 +436,7 @@ def run_gpu_arm(args):
                 'traffic = dram read + write bytes per launch from the ncu capture under profiles/',
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = run_cpu_arm(args, steps=1, warmup=1)
+        line['cpu_baseline'] = run_cpu_arm(args, steps=1, warmup=1, sample_per_core=16)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
