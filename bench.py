@@ -80,25 +80,26 @@ def _cpu_code_one(job):
 
 def cpu_pipeline(images, weights, table, map_mean, cores, pool, which):
     """CPU restatement of one batch: encoder -> centre/quantize -> coder (encode + decode per map, as the
-    reference's compress_lossless does) -> decoder -> cast. Returns (seconds, bits, reconstruction)."""
+    reference's compress_lossless does) -> decoder -> cast. The transforms run in mini-batches of 4 on all cores
+    (torch threads), the coder of ALL images then runs one image per worker process on all cores.
+    Returns (seconds, bits, reconstruction)."""
     import torch
     from oracle import glue, transforms
     torch.set_num_threads(cores)
     t0 = time.perf_counter()
     rec = numpy.zeros(images.shape, dtype=numpy.uint8)
-    bits = 0
     mean = map_mean.reshape((1, 1, 1, -1))
-    pending = []
+    (planar, quantized) = ([], [])
     for i0 in range(0, images.shape[0], 4):          # reconstructing_eae_kodak.py:624 batch_size = 4
         x = images[i0:i0 + 4, :, :, None].astype(numpy.float32)
         y = transforms.encoder(x, weights, False)
         cq = glue.quantize_per_map(y - mean, numpy.ones(128, dtype=numpy.float32))
         idx = glue.cast_float_to_int16(cq)
-        planar = [numpy.ascontiguousarray(idx[j].reshape(-1, 128).T) for j in range(idx.shape[0])]
-        # the coder of these images runs in the worker processes while the main process goes on with the transforms
-        pending.append(pool.map_async(_cpu_code_one, [(p, table, which) for p in planar]))
-        rec[i0:i0 + 4] = glue.cast_bt601(transforms.decoder(cq + mean, weights, False))[..., 0]
-    bits = sum(sum(job.get()) for job in pending)
+        planar += [numpy.ascontiguousarray(idx[j].reshape(-1, 128).T) for j in range(idx.shape[0])]
+        quantized.append(cq)
+    bits = sum(pool.map(_cpu_code_one, [(p, table, which) for p in planar]))
+    for (k, cq) in enumerate(quantized):
+        rec[4*k:4*k + 4] = glue.cast_bt601(transforms.decoder(cq + mean, weights, False))[..., 0]
     return (time.perf_counter() - t0, bits, rec)
 
 
@@ -418,8 +419,8 @@ def run_gpu_arm(args):
               'fp32': {'gemm_conv': 0., 'gemm_tconv': 0., 'gemm_gdn': 0., 'gemm_thin': 0.}}[args.math]
     executed = sum(GFLOP_PER_IMAGE[k]*passes[k] for k in GFLOP_PER_IMAGE)*scale*n*args.steps/gemm_ms if gemm_ms > 0 else 0.
     # DRAM bytes per launch of this kernel from the committed ncu capture of this workload
-    # (profiles/r01_ncu_full_gemm_layers_final.md: 13 launches per step, 1810 MB per 24-image step).
-    traffic = 1810.1e6/13.*(n/24.)*scale if args.math != 'fp32' else None
+    # (profiles/r01_ncu_full_gemm_layers_final.md: 13 launches per step, 1802 MB per 24-image step).
+    traffic = 1801.7e6/13.*(n/24.)*scale if args.math != 'fp32' else None
     line['roofline'] = {
         'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
         'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',

@@ -50,7 +50,7 @@ def main():
         wr = float(r[c['dram__bytes_write.sum']])
         h = float(r[c['sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg']])
         cy = float(r[c['sm__cycles_elapsed.avg']])
-        kern = 'v4' if 'umma4' in r[c['Kernel Name']] else 'v3'
+        kern = 'v4' if 'umma4' in r[c['Kernel Name']] else ('v5' if 'umma5' in r[c['Kernel Name']] else 'v3')
         print('| {} | {} | {} | {:.1f} | {:.1f} | {:.1f} | {:.1f} % | {:.0f} | {:.0f} |'.format(
             NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, 100.*h/(4.*cy), ALG[k]*images/d*1e3, EXE[k]*images/d*1e3))
         tt += d; tr += rd; tw += wr; ta += ALG[k]*images; te += EXE[k]*images
