@@ -433,12 +433,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
                  :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
 
 __global__ void __launch_bounds__(kUmmaThreads2, 1)
 gemm_umma2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
@@ -732,99 +726,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
-// ---- fused GDN / IGDN tail (version 4) ---------------------------------------------------------------------
-// NRM_h = (x_h^2) gamma for both 128-row halves h, x = accumulator + bias, as 8 steps j = 4 h + kc over the four
-// 32-channel chunks of x^2, in the shared memory the main loop has just released:
-//   stage s = j & 1 at area + s * 64K = { (x^2)_hi 16K | (x^2)_lo 16K | gamma_hi chunk 16K | gamma_lo chunk 16K }
-//     (conversion set k owns stage k, as it owns TMEM slot k in the main loop; the TMA producer refills its gamma part)
-//   area + 128K .. 192K : output staging of half 0;  area + 0 .. 64K : output staging of half 1 (after the last MMA)
-// The halves are pipelined: once the four steps of half 0 are done (nrm0_full) the conversion warps normalise,
-// stage and STORE half 0 between their two remaining conversions, while the tensor pipe works on half 1. Only
-// half 1's read-out and store remain after the last MMA.
-struct GdnTail {
-    uint8_t* area;
-    uint64_t* g_full;      // [2] gamma chunk of the step landed in stage s
-    uint64_t* x_ready;     // [2] x^2 of the step written to stage s (4 arrivals: one per conversion warp of the set)
-    uint64_t* x_free;      // [2] the MMAs that read stage s completed
-    uint64_t* acc_full;
-    uint64_t* nrm0_full;
-    uint64_t* nrm_full;
-};
-__device__ __forceinline__ void gdn_tail_init(const GdnTail& t)
-{
-    for (int s = 0; s < 2; s++) { mbar_init(&t.g_full[s], 1); mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
-    mbar_init(t.nrm0_full, 1);
-}
-// TMA producer thread, after its last main-loop load.
-__device__ __forceinline__ void gdn_tail_producer(const GdnTail& t, const CUtensorMap* map_g_hi, const CUtensorMap* map_g_lo,
-                                                  uint32_t* error_flag)
-{
-    // the stages alias the buffers of the main loop: wait until every main MMA has completed
-    if (!mbar_wait(t.acc_full, 0, error_flag, 0)) return;
-    for (int j = 0; j < 8; j++) {
-        const int s = j & 1;
-        if (j >= 2 && !mbar_wait(&t.x_free[s], (uint32_t)((j >> 1) - 1) & 1u, error_flag, 0)) return;
-        uint8_t* g = t.area + s * 4 * kTileBytes + 2 * kTileBytes;
-        mbar_expect_tx(&t.g_full[s], 2 * kTileBytes);
-        tma_load_3d(g, map_g_hi, &t.g_full[s], (j & 3) * kChunkK, 0, 0);
-        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[s], (j & 3) * kChunkK, 0, 0);
-    }
-}
-// MMA warp (all lanes; one elected lane issues).
-__device__ __forceinline__ void gdn_tail_mma(const GdnTail& t, uint32_t* error_flag)
-{
-    for (int j = 0; j < 8; j++) {
-        const int h = j >> 2, kc = j & 3, s = j & 1;
-        bool ok = mbar_wait(&t.x_ready[s], (uint32_t)(j >> 1) & 1u, error_flag, 1);
-        if (ok) ok = mbar_wait(&t.g_full[s], (uint32_t)(j >> 1) & 1u, error_flag, 1);
-        if (!__all_sync(0xFFFFFFFFu, ok)) return;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-            const uint32_t st = smem_u32(t.area + s * 4 * kTileBytes);
-            const uint32_t d = kTmemBase0 + (h ? kCol3Nrm1 : kCol3Nrm0);
-            #pragma unroll
-            for (int k = 0; k < kChunkK / 8; k++) {
-                const uint64_t x_hi = make_desc(st + k * 32), x_lo = make_desc(st + kTileBytes + k * 32);
-                const uint64_t g_hi = make_desc(st + 2 * kTileBytes + k * 32);
-                umma_tf32(d, x_hi, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
-                umma_tf32(d, x_lo, g_hi, 1u);
-                umma_tf32(d, x_hi, make_desc(st + 3 * kTileBytes + k * 32), 1u);
-            }
-            umma_commit(&t.x_free[s]);
-            if (j == 3) umma_commit(t.nrm0_full);
-            if (j == 7) umma_commit(t.nrm_full);
-        }
-        __syncwarp();
-    }
-}
-// One conversion step of set `set`: x = acc + bias from the chunk already requested into r, x^2 split into the stage.
-__device__ __forceinline__ void gdn_tail_square(const GdnTail& t, int set, int row, int lane, int c0, const uint32_t* r,
-                                                const float* __restrict__ bias)
-{
-    uint8_t* rowp = t.area + set * 4 * kTileBytes + row * 128;
-    #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
-                               __uint_as_float(r[4 * c + 3]));
-        if (bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
-            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-        }
-        x.x *= x.x; x.y *= x.y; x.z *= x.z; x.w *= x.w;
-        float4 xl;      // hi = the value itself (the tensor core truncates), lo = x - trunc_tf32(x)
-        xl.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        xl.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        xl.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        xl.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-        *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = x;
-        *reinterpret_cast<float4*>(rowp + kTileBytes + ((c ^ (row & 7)) << 4)) = xl;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&t.x_ready[set]);
-}
-
 // Epilogue staging shared by versions 3 and 4: this thread's row, this set's 64 channels of both halves:
 // TMEM (accumulator and, when GDN / IGDN is fused, the norm accumulator) -> bias, normalisation -> shared memory
 // (half h at smem + h * stage_bytes, four swizzled [128 x 32] sub-tiles). The TMEM reads of the next 32-column
@@ -884,22 +785,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* smem, int stage_bytes, uint3
     }
 }
 
-// This set's 64 channels of ONE half -> `stage` (64 KB, four swizzled [128 x 32] sub-tiles), and the coalesced store
-// of a staged half (version 4 geometry: 16 x 16 positions per tile, half h = rows 8 h .. 8 h + 7).
-__device__ __forceinline__ void stage_half(uint8_t* stage, int h, uint32_t lane_base, int set, int row, bool gdn, int fuse,
-                                           const float* __restrict__ bias, const float* __restrict__ beta)
-{
-    uint32_t ra[32], na[32], rb[32], nb[32];
-    const uint32_t acc = lane_base + (h ? kCol3Acc1 : kCol3Acc0) + set * 64, nrm = lane_base + (h ? kCol3Nrm1 : kCol3Nrm0) + set * 64;
-    tmem_ld32_nowait(acc, ra);
-    if (gdn) tmem_ld32_nowait(nrm, na);
-    tmem_ld_wait();
-    tmem_ld32_nowait(acc + 32, rb);
-    if (gdn) tmem_ld32_nowait(nrm + 32, nb);
-    stage_chunk(stage + (set * 2) * kTileBytes + row * 128, row, set * 64, ra, na, gdn, fuse, bias, beta);
-    tmem_ld_wait();
-    stage_chunk(stage + (set * 2 + 1) * kTileBytes + row * 128, row, set * 64 + 32, rb, nb, gdn, fuse, bias, beta);
-}
+// Coalesced store of a staged half (16 x 16 positions per tile, half h = rows 8 h .. 8 h + 7).
 struct OutGeom4 {
     float* out;
     int img, a0, b0, Hg, Wg, Hout, Wout, out_mul, out_r, out_s, out_split;
@@ -929,6 +815,177 @@ __device__ __forceinline__ void store_half4(const OutGeom4& g, const uint8_t* st
     }
 }
 
+// ---- fused GDN / IGDN tail, tensor-memory operand form (versions 3 and 4) ------------------------------------
+// The shared-memory-operand GDN MMAs of the first tail ran at ~113 cycles each instead of 64 (A and B both stream
+// from shared memory: 128 B/clk, the whole port). Here the A operand ((x^2)_hi | (x^2)_lo of a 32-channel chunk) goes
+// to a TMEM slot, as in the main loop, and only gamma streams from shared memory, where it is resident:
+//   TMEM   [0,128) ACC0   [128,256) ACC1   [256,384) NRM0   [384,512) two A slots {hi 32 | lo 32}
+//          half 1's norm is accumulated in ACC0's columns: each conversion set copies its 64 channels of x_0 = ACC0 + bias
+//          to the output staging area right after its two half-0 conversions (acc0_read), before step 4 can overwrite them
+//   smem   area + kc * 32K : gamma chunk kc {hi 16K | lo 16K} (loaded once);  area + 128K : staging of half 0;
+//          area + 0 : staging of half 1 (after the last MMA)
+// Order per conversion set k (steps j = k + 2 i): i = 0, 1 (half 0), copy-out of x_0, i = 2, 3 (half 1), then half 0 is
+// normalised in place from NRM0, stored, and half 1 follows after the last MMA.
+struct GdnTailTs {
+    uint8_t* area;
+    uint64_t* g_full;      // [4] gamma chunk kc landed (single use)
+    uint64_t* x_ready;     // [2] A slot k written (one arrival per conversion warp of set k)
+    uint64_t* x_free;      // [2] the MMAs that read slot k completed
+    uint64_t* acc0_read;   // x_0 copied out of TMEM (8 arrivals: every conversion warp)
+    uint64_t* acc_full;
+    uint64_t* nrm0_full;
+    uint64_t* nrm_full;
+};
+__device__ __forceinline__ void gdn_tail_ts_init(const GdnTailTs& t)
+{
+    for (int s = 0; s < 4; s++) mbar_init(&t.g_full[s], 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
+    mbar_init(t.acc0_read, 8);
+    mbar_init(t.nrm0_full, 1);
+}
+__device__ __forceinline__ void gdn_tail_ts_producer(const GdnTailTs& t, const CUtensorMap* map_g_hi, const CUtensorMap* map_g_lo,
+                                                     uint32_t* error_flag)
+{
+    if (!mbar_wait(t.acc_full, 0, error_flag, 0)) return;      // gamma lands on the buffers of the main loop
+    for (int kc = 0; kc < 4; kc++) {
+        uint8_t* g = t.area + kc * 2 * kTileBytes;
+        mbar_expect_tx(&t.g_full[kc], 2 * kTileBytes);
+        tma_load_3d(g, map_g_hi, &t.g_full[kc], kc * kChunkK, 0, 0);
+        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[kc], kc * kChunkK, 0, 0);
+    }
+}
+__device__ __forceinline__ void gdn_tail_ts_mma(const GdnTailTs& t, uint32_t* error_flag)
+{
+    for (int j = 0; j < 8; j++) {
+        const int h = j >> 2, kc = j & 3, sl = j & 1;
+        bool ok = mbar_wait(&t.x_ready[sl], (uint32_t)(j >> 1) & 1u, error_flag, 1);
+        if (ok) ok = mbar_wait(&t.g_full[kc], 0, error_flag, 1);
+        if (ok && j == 4) ok = mbar_wait(t.acc0_read, 0, error_flag, 1);
+        if (!__all_sync(0xFFFFFFFFu, ok)) return;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint32_t g = smem_u32(t.area + kc * 2 * kTileBytes);
+            const uint32_t d = kTmemBase0 + (h ? kCol3Acc0 : kCol3Nrm0);
+            const uint32_t a_hi = kTmemBase0 + kCol3Nrm1 + 64u * (uint32_t)sl, a_lo = a_hi + 32u;
+            #pragma unroll
+            for (int k = 0; k < kChunkK / 8; k++) {
+                const uint64_t g_hi = make_desc(g + k * 32);
+                umma_tf32_ts(d, a_hi + 8 * k, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
+                umma_tf32_ts(d, a_lo + 8 * k, g_hi, 1u);
+                umma_tf32_ts(d, a_hi + 8 * k, make_desc(g + kTileBytes + k * 32), 1u);
+            }
+            umma_commit(&t.x_free[sl]);
+            if (j == 3) umma_commit(t.nrm0_full);
+            if (j == 7) umma_commit(t.nrm_full);
+        }
+        __syncwarp();
+    }
+}
+// Conversion warps of set `set` (thread = accumulator row): conversions, copy-out, normalisation and stores of both halves.
+__device__ __forceinline__ bool gdn_tail_ts_run(const GdnTailTs& t, int set, int row, int lane, int wq, uint32_t lane_base,
+                                                int fuse, const float* __restrict__ bias, const float* __restrict__ beta,
+                                                const OutGeom4& geom, uint32_t* error_flag, long long* stamp)
+{
+    uint32_t r[32], nr[32];
+    uint8_t* stage0 = t.area + 8 * kTileBytes;
+    uint8_t* stage1 = t.area;
+    bool ok = mbar_wait(t.acc_full, 0, error_flag, 3);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (stamp && threadIdx.x == 64) stamp[4] = clock64();
+    const uint32_t slot = lane_base + kCol3Nrm1 + 64u * (uint32_t)set;
+    #pragma unroll
+    for (int i = 0; i < 4 && ok; i++) {
+        const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
+        tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
+        if (i >= 1) ok = mbar_wait(&t.x_free[set], (uint32_t)(i - 1) & 1u, error_flag, 7);      // MMAs of step j - 2
+        tmem_ld_wait();
+        if (!ok) break;
+        if (i >= 1) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        #pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                   __uint_as_float(r[4 * c + 3]));
+            if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c));
+                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+            }
+            r[4 * c] = __float_as_uint(x.x * x.x); r[4 * c + 1] = __float_as_uint(x.y * x.y);
+            r[4 * c + 2] = __float_as_uint(x.z * x.z); r[4 * c + 3] = __float_as_uint(x.w * x.w);
+        }
+        tmem_st32(slot, r);           // hi = the value itself (the tensor core truncates), lo = x^2 - trunc_tf32(x^2)
+        #pragma unroll
+        for (int q = 0; q < 32; q++) r[q] = __float_as_uint(__uint_as_float(r[q]) - __uint_as_float(r[q] & 0xFFFFE000u));
+        tmem_st32(slot + 32u, r);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t.x_ready[set]);
+        if (i == 1) {
+            // x_0 = ACC0 + bias of this set's 64 channels -> staging of half 0; ACC0's columns then belong to NRM1
+            #pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int c1 = set * 64 + cc * 32;
+                tmem_ld32(lane_base + kCol3Acc0 + c1, r);
+                uint8_t* sub = stage0 + (c1 / 32) * kTileBytes + row * 128;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    float4 x = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                           __uint_as_float(r[4 * c + 3]));
+                    if (bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c1 + 4 * c));
+                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                    }
+                    *reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4)) = x;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t.acc0_read);
+        }
+    }
+    // ---- half 0: normalise the staged x_0 in place with NRM0, store
+    if (ok) ok = mbar_wait(t.nrm0_full, 0, error_flag, 4);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    #pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+        const int c1 = set * 64 + cc * 32;
+        tmem_ld32(lane_base + kCol3Nrm0 + c1, nr);
+        uint8_t* sub = stage0 + (c1 / 32) * kTileBytes + row * 128;
+        #pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float4* px = reinterpret_cast<float4*>(sub + ((c ^ (row & 7)) << 4));
+            float4 x = *px;
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c1 + 4 * c));
+            const float n0 = __uint_as_float(nr[4 * c]) + be.x, n1 = __uint_as_float(nr[4 * c + 1]) + be.y;
+            const float n2 = __uint_as_float(nr[4 * c + 2]) + be.z, n3 = __uint_as_float(nr[4 * c + 3]) + be.w;
+            if (fuse == 1) {
+                x.x *= rsqrt_fast(n0); x.y *= rsqrt_fast(n1); x.z *= rsqrt_fast(n2); x.w *= rsqrt_fast(n3);
+            } else {
+                x.x *= n0 * rsqrt_fast(n0); x.y *= n1 * rsqrt_fast(n1); x.z *= n2 * rsqrt_fast(n2); x.w *= n3 * rsqrt_fast(n3);
+            }
+            *px = x;
+        }
+    }
+    named_bar_sync(1, 256);     // both sets finished half 0
+    store_half4(geom, stage0, 0, wq, lane, ok);
+    // ---- half 1: ACC1 and NRM1 (in ACC0's columns) -> staging -> store
+    if (ok) ok = mbar_wait(t.nrm_full, 0, error_flag, 4);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+    #pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+        const int c1 = set * 64 + cc * 32;
+        tmem_ld32_nowait(lane_base + kCol3Acc1 + c1, r);
+        tmem_ld32_nowait(lane_base + kCol3Acc0 + c1, nr);
+        tmem_ld_wait();
+        stage_chunk(stage1 + (c1 / 32) * kTileBytes + row * 128, row, c1, r, nr, true, fuse, bias, beta);
+    }
+    named_bar_sync(1, 256);
+    if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+    store_half4(geom, stage1, 1, wq, lane, ok);
+    return ok;
+}
+
 __global__ void __launch_bounds__(kUmmaThreads3, 1)
 gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
@@ -945,9 +1002,9 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* acc_full = bars + 3 * kStages3;
     uint64_t* nrm_full = bars + 3 * kStages3 + 1;
     uint64_t* img_full = bars + 3 * kStages3 + 2;
-    const GdnTail tail{smem, bars + 12 /* g_full[2] */, bars + 14 /* x_ready[2] */, bars + 16 /* x_free[2] */, acc_full,
-                       bars + 18 /* nrm0_full */, nrm_full};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    const GdnTailTs tail{smem, bars + 12 /* g_full[4] */, bars + 16 /* x_ready[2] */, bars + 18 /* x_free[2] */,
+                         bars + 20 /* acc0_read */, acc_full, bars + 21 /* nrm0_full */, nrm_full};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
@@ -967,7 +1024,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
         mbar_init(img_full, 1);
-        gdn_tail_init(tail);
+        gdn_tail_ts_init(tail);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1017,7 +1074,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (p.exact_main) tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full[s], kc * kChunkK, 0, tap.w_tap);
                 }
             }
-            if (n_gdn) gdn_tail_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
+            if (n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the loop, one elected lane issues (warp-uniform operands) =====
@@ -1048,7 +1105,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             __syncwarp();
         }
-        if (n_gdn) gdn_tail_mma(tail, p.error_flag);
+        if (n_gdn) gdn_tail_ts_mma(tail, p.error_flag);
     } else {
         // ===== warps 2..9: two conversion / epilogue sets (set = iteration parity) =====
         const int quarter = warp & 3;
@@ -1056,7 +1113,7 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         bool ok = true;
-        uint32_t r[32], hi[32];
+        uint32_t r[32];
         for (int it = set; it < n_total && ok; it += 2) {
             const int s = it % kStages3;
             ok = mbar_wait(&full[s], (it / kStages3) & 1, p.error_flag, 2);
@@ -1119,39 +1176,10 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             mbar_arrive(&split[s]);
         }
         if (n_gdn) {
-            // ---- fused GDN / IGDN (tile geometry 16 x 16, as in version 4): this set converts steps j = set + 2 i; half 0 is
-            // normalised, staged and stored while the tensor pipe contracts half 1
+            // ---- fused GDN / IGDN (tile geometry 16 x 16, as in version 4)
             const int wq = warp - 2;
             const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
-            uint8_t* stage0 = smem + 2 * kStageBytes3;
-            uint8_t* stage1 = smem;
-            if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-            #pragma unroll
-            for (int i = 0; i < 4 && ok; i++) {
-                const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
-                tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                if (i >= 1) ok = mbar_wait(&tail.x_free[set], (uint32_t)(i - 1) & 1u, p.error_flag, 7);
-                tmem_ld_wait();
-                if (!ok) break;
-                gdn_tail_square(tail, set, row, lane, c0, r, p.bias);
-                if (i == 3) {
-                    ok = mbar_wait(tail.nrm0_full, 0, p.error_flag, 4);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (!ok) break;
-                    stage_half(stage0, 0, lane_base, set, row, true, p.fuse, p.bias, p.beta);
-                    named_bar_sync(1, 256);
-                    store_half4(geom, stage0, 0, wq, lane, ok);
-                }
-            }
-            if (ok) ok = mbar_wait(nrm_full, 0, p.error_flag, 4);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
-            stage_half(stage1, 1, lane_base, set, row, true, p.fuse, p.bias, p.beta);
-            named_bar_sync(1, 256);
-            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
-            store_half4(geom, stage1, 1, wq, lane, ok);
+            if (ok) ok = gdn_tail_ts_run(tail, set, row, lane, wq, lane_base, p.fuse, p.bias, p.beta, geom, p.error_flag, stamp);
         } else {
         if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1278,9 +1306,9 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* split = bars + 12;           // [2] TMEM A slot written (128 arrivals: one conversion set)
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
-    const GdnTail tail{smem, bars + 18 /* g_full[2] */, bars + 20 /* x_ready[2] */, bars + 22 /* x_free[2] */, acc_full,
-                       bars + 24 /* nrm0_full */, nrm_full};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+    const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[2] */, bars + 24 /* x_free[2] */,
+                         bars + 26 /* acc0_read */, acc_full, bars + 27 /* nrm0_full */, nrm_full};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
@@ -1294,7 +1322,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&u_full[s], 1); mbar_init(&split[s], 4); }     // one arrival per conversion warp
-        gdn_tail_init(tail);
+        gdn_tail_ts_init(tail);
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1353,7 +1381,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 tma_load_3d(st, &map_b_hi, &b_full[s], kc * kChunkK, 0, tap.w_tap);
                 if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &b_full[s], kc * kChunkK, 0, tap.w_tap);
             }
-            if (ok && n_gdn) gdn_tail_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
+            if (ok && n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
@@ -1388,7 +1416,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 }
                 __syncwarp();
             }
-            if (ok && n_gdn) gdn_tail_mma(tail, p.error_flag);
+            if (ok && n_gdn) gdn_tail_ts_mma(tail, p.error_flag);
         }
     } else {
         // ===== warps 2..9: two conversion / epilogue sets; set k owns TMEM A slot k and the iterations of parity k
@@ -1446,39 +1474,10 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         }
         const int wq = warp - 2;
         const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
-        uint8_t* stage0 = smem + (n_gdn ? 2 : 0) * kGdnStageBytes4;     // half 0: above the two GDN stages when GDN is fused
-        uint8_t* stage1 = smem + (n_gdn ? 0 : 1) * kGdnStageBytes4;
+        uint8_t* stage0 = smem;                          // un-fused epilogue: both halves staged side by side
+        uint8_t* stage1 = smem + kGdnStageBytes4;
         if (ok && n_gdn) {
-            // ---- fused GDN / IGDN: this set converts steps j = set + 2 i; half 0 leaves while half 1 is contracted
-            ok = mbar_wait(acc_full, 0, p.error_flag, 3);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-            #pragma unroll
-            for (int i = 0; i < 4 && ok; i++) {
-                const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
-                tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
-                if (i >= 1) ok = mbar_wait(&tail.x_free[set], (uint32_t)(i - 1) & 1u, p.error_flag, 7);    // MMAs of step j - 2
-                tmem_ld_wait();
-                if (!ok) break;
-                gdn_tail_square(tail, set, row, lane, c0, r, p.bias);
-                if (i == 3) {
-                    // this set's conversions are done; the norm of half 0 has been complete since step 3: normalise,
-                    // stage and store half 0 while the tensor pipe contracts half 1
-                    ok = mbar_wait(tail.nrm0_full, 0, p.error_flag, 4);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (!ok) break;
-                    stage_half(stage0, 0, lane_base, set, row, true, p.fuse, p.bias, p.beta);
-                    named_bar_sync(1, 256);     // both sets staged half 0
-                    store_half4(geom, stage0, 0, wq, lane, ok);
-                }
-            }
-            if (ok) ok = mbar_wait(nrm_full, 0, p.error_flag, 4);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
-            stage_half(stage1, 1, lane_base, set, row, true, p.fuse, p.bias, p.beta);
-            named_bar_sync(1, 256);
-            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
-            store_half4(geom, stage1, 1, wq, lane, ok);
+            ok = gdn_tail_ts_run(tail, set, row, lane, wq, lane_base, p.fuse, p.bias, p.beta, geom, p.error_flag, stamp);
         } else {
             if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
