@@ -48,11 +48,15 @@ def main():
         d = float(r[c['gpu__time_duration.sum']])
         rd = float(r[c['dram__bytes_read.sum']])
         wr = float(r[c['dram__bytes_write.sum']])
-        h = float(r[c['sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg']])
-        cy = float(r[c['sm__cycles_elapsed.avg']])
+        try:
+            h = float(r[c['sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg']])
+            cy = float(r[c['sm__cycles_elapsed.avg']])
+            active = '{:.1f} %'.format(100.*h/(4.*cy))
+        except ValueError:
+            active = 'n/a (counter not collected in this pass)'
         kern = 'v4' if 'umma4' in r[c['Kernel Name']] else ('v5' if 'umma5' in r[c['Kernel Name']] else 'v3')
-        print('| {} | {} | {} | {:.1f} | {:.1f} | {:.1f} | {:.1f} % | {:.0f} | {:.0f} |'.format(
-            NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, 100.*h/(4.*cy), ALG[k]*images/d*1e3, EXE[k]*images/d*1e3))
+        print('| {} | {} | {} | {:.1f} | {:.1f} | {:.1f} | {} | {:.0f} | {:.0f} |'.format(
+            NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, active, ALG[k]*images/d*1e3, EXE[k]*images/d*1e3))
         tt += d; tr += rd; tw += wr; ta += ALG[k]*images; te += EXE[k]*images
     print('| **all 13 launches** | | | **{:.1f}** | **{:.1f}** | **{:.1f}** | | **{:.0f}** | **{:.0f}** |'.format(
         tt, tr, tw, ta/tt*1e3, te/tt*1e3))
