@@ -17,7 +17,8 @@ EAE_NB_MAPS = 128
 MATH_FP32_SIMT = 0
 MATH_TF32X3 = 1
 MATH_TF32 = 2
-MATH_NAMES = {'fp32': MATH_FP32_SIMT, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32}
+MATH_MIXED = 3
+MATH_NAMES = {'fp32': MATH_FP32_SIMT, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32, 'mixed': MATH_MIXED}
 
 ERR_NULL = -1
 ERR_UNARY_LENGTH = -2

@@ -17,6 +17,7 @@ struct eae_codec {
     int device = 0;
     int learned = 0;   // are_bin_widths_learned: 4 GDN/IGDN instead of 6
     int math = EAE_MATH_FP32_SIMT;
+    bool exact_now = true; // do the contractions of the transform being run use the 3-way split (set per chunk)
     int umma_mask = 0xF;   // which layer kinds run on tensor cores (debug: env EAE_UMMA_LAYERS)
     uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
@@ -196,7 +197,7 @@ int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw
     if (c->math == EAE_MATH_FP32_SIMT || !((c->umma_mask >> kind) & 1)) return launch_gemm_simt(plan, st);
     // GDN / IGDN always use the split contraction: a single-pass TF32 norm would put a 2^-12 relative
     // error on every activation, for 4 % of the FLOPs.
-    const bool exact = c->math == EAE_MATH_TF32X3 || kind == kLayerGdn;
+    const bool exact = c->exact_now || kind == kLayerGdn;
     return launch_gemm_umma(plan, uw, gamma, exact, st);
 }
 
@@ -299,6 +300,7 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
                  cudaStream_t st)
 {
     const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8;
+    c->exact_now = c->math == EAE_MATH_TF32X3 || c->math == EAE_MATH_MIXED;      // the indices are decided here
     float* A = c->bufA.as<float>();
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
@@ -325,6 +327,7 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
                  float* out_f32_dev, cudaStream_t st)
 {
     const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8, H3 = h / 16, W3 = w / 16;
+    c->exact_now = c->math == EAE_MATH_TF32X3;
     float* P = c->bufA.as<float>();
     float* x1 = c->buf1.as<float>();
     float* x2 = c->buf2.as<float>();
@@ -336,7 +339,12 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
     }
     EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), 3, c->bias[3].as<float>(), x2, 4, n, st));
     EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), 4, c->bias[4].as<float>(), x1, 5, n, st));
-    // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias: per-pixel tap contributions, then col2im
+    // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias. Kernel version 6 contracts, gathers and casts in one launch;
+    // otherwise: per-pixel tap contributions, then col2im.
+    if (c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() >= 6) {
+        ProfScope prof(kProfGemmThin, st);
+        return launch_tconv9s4_fused(x1, umma_weights(c, 5, 1), out_u8_dev, out_f32_dev, n, (int)h, (int)w, c->exact_now, st);
+    }
     {
         GemmPlan p = base_plan(x1, H1, W1, 128, c->w6m.as<float>(), nullptr, P, n);
         EAE_TRY(run_layer(c, &p, 1, kLayerThin, umma_weights(c, 5, 1), -1, false, p.M, st));
@@ -733,7 +741,7 @@ extern "C" int eae_codec_destroy(eae_codec_t* c)
 extern "C" int eae_codec_set_math(eae_codec_t* c, int mode)
 {
     if (!c) { set_error("NULL codec"); return EAE_ERR_NULL; }
-    if (mode != EAE_MATH_FP32_SIMT && mode != EAE_MATH_TF32X3 && mode != EAE_MATH_TF32) {
+    if (mode != EAE_MATH_FP32_SIMT && mode != EAE_MATH_TF32X3 && mode != EAE_MATH_TF32 && mode != EAE_MATH_MIXED) {
         set_error("unknown math mode %d", mode); return EAE_ERR_ARGUMENT;
     }
     if (mode != EAE_MATH_FP32_SIMT) EAE_TRY(umma_available());

@@ -1455,7 +1455,13 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x)
+            // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x). Single pass: round to nearest
+            // instead (add half a TF32 ulp to the magnitude before the truncation) - truncation shrinks every product by
+            // 2^-12 on average, a bias that does not average out over the ~1 200 terms of a sum.
+            if (!p.exact_main) {
+                #pragma unroll
+                for (int i = 0; i < 32; i++) { r[i] += 0x1000u; hi[i] += 0x1000u; }
+            }
             tmem_st32(slot, r);
             tmem_st32(slot + 64u, hi);
             if (p.exact_main) {
@@ -1701,6 +1707,10 @@ gemm_umma5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint32_t slot = lane_base + kCol5Slots + 64u * (uint32_t)(it & 1);
+            if (!p.exact_main && !p.conv1) {      // single pass: round to nearest TF32 (see version 4)
+                #pragma unroll
+                for (int i = 0; i < 32; i++) r[i] += 0x1000u;
+            }
             tmem_st32(slot, r);
             if (p.exact_main && !p.conv1) {
                 #pragma unroll
@@ -1787,6 +1797,219 @@ gemm_umma5_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.times[(size_t)blockIdx.x * 3 + 2] = t;
     }
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols5) : "memory");
+    }
+}
+
+// =================================================================================================
+// Version 6: the LAST layer (conv2d_transpose k9 s4, 128 -> 1, components.py:79-84) with its col2im gather and the
+// BT.601 cast (tools.py:61-93) inside the kernel.
+//
+// Measured on version 5 (profiles/r01_ncu_full_gemm_layers_final.md): the per-position tap matrix [positions, 128] is
+// written to HBM (257 MB per 24 images) only to be read back by col2im_k9s4_kernel (another 302 MB + 94 us), for 9 MB
+// of pixels. Here a CTA contracts a tile of 8 x 16 positions (as version 5: thread = position = TMEM lane, two CTAs
+// per SM), dumps the 81 tap columns of its accumulator to shared memory and gathers the pixels of the 6 x 14 pixel
+// blocks whose contributing positions all lie inside the tile: pixel row oy = 4 q + r - 2 (block q, r in [0, 4))
+// receives position q through ky = r, q - 1 through ky = r + 4 and, for r = 0, q - 2 through ky = 8 - so blocks
+// [q0, q0 + 6) need positions [q0 - 2, q0 + 6). Tiles overlap by two positions (65 % of the contracted rows are
+// new); positions outside the layer's input are zero-filled by TMA and contribute exact zeros, which is what the
+// skip in col2im_k9s4_kernel amounts to. The sum runs in that kernel's order, so the two paths agree bit for bit.
+// MMA N = 96 (81 taps used). HBM traffic: the activations once (the overlap is served by L2) + the pixels.
+constexpr int kColStride6 = 87;                    // odd: the thread-per-row dump is conflict-free
+constexpr int kBlkY6 = 6, kBlkX6 = 14;             // pixel blocks (4 x 4 pixels) a tile completes
+constexpr int kSmemBytes6 = kMainBytes5 + 256 + 1024;
+constexpr uint32_t kInstrDescN96 = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+static_assert(kTileM * kColStride6 * 4 <= kMainBytes5, "tap columns alias the stages");
+
+struct UmmaParams6 {
+    int kchunks;
+    int tiles_x, tiles_y;
+    int H, W;                // output image
+    uint8_t* out_u8;         // [n, H, W] or NULL
+    float* out_f32;          // [n, H, W] un-clipped, or NULL
+    int exact_main;
+    uint32_t* error_flag;
+};
+
+__device__ __forceinline__ void umma_tf32_ts_n96(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kInstrDescN96), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+tconv9s4_umma6_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
+                      const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ UmmaParams6 p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMainBytes5);
+    uint64_t* full = bars;                 // [2] stage landed
+    uint64_t* done = bars + 2;             // [2] MMAs of the iteration that used the stage completed
+    uint64_t* split = bars + 4;            // [2] TMEM A slot written (one arrival per conversion warp)
+    uint64_t* acc_full = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int q0 = (trem / p.tiles_x) * kBlkY6, p0 = (trem % p.tiles_x) * kBlkX6;      // first pixel block of the tile
+    const int a0 = q0 - 2, b0 = p0 - 2;                                                // first position of the tile
+    constexpr int kStageBytes = 3 * kTileBytes;                                         // A | B_hi | B_lo
+    const int n_main = p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], 1); mbar_init(&split[s], 4); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols5) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;      // 0 or 256: two CTAs share the SM
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            bool ok = true;
+            for (int it = 0; it < n_main && ok; it++) {
+                const int s = it & 1;
+                if (it >= 2) ok = mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u, p.error_flag, 0);
+                if (!ok) break;
+                uint8_t* st = smem + s * kStageBytes;
+                mbar_expect_tx(&full[s], kTileBytes + (p.exact_main ? 2 : 1) * 96 * 128);
+                tma_load_5d(st, &map_a, &full[s], it * kChunkK, b0, a0, 0, img);        // rows outside the input: zeros
+                tma_load_3d(st + kTileBytes, &map_b_hi, &full[s], it * kChunkK, 0, 0);
+                if (p.exact_main) tma_load_3d(st + 2 * kTileBytes, &map_b_lo, &full[s], it * kChunkK, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+        const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        bool ok = true;
+        for (int it = 0; it < n_main && ok; it++) {
+            const int s = it & 1;
+            ok = __all_sync(0xFFFFFFFFu, mbar_wait(&split[s], (uint32_t)(it >> 1) & 1u, p.error_flag, 1));
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t st = smem_u32(smem + s * kStageBytes + kTileBytes);
+                const uint32_t a_hi = tb + kCol5Slots + 64u * (uint32_t)s, a_lo = a_hi + 32u;
+                #pragma unroll
+                for (int k = 0; k < kChunkK / 8; k++) {
+                    const uint64_t b_hi = make_desc(st + k * 32);
+                    umma_tf32_ts_n96(tb, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
+                    if (p.exact_main) {
+                        umma_tf32_ts_n96(tb, a_lo + 8 * k, b_hi, 1u);
+                        umma_tf32_ts_n96(tb, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
+                    }
+                }
+                umma_commit(&done[s]);
+                if (it == n_main - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== warps 2..5: operand conversion, then the gather (thread = position = accumulator row = TMEM lane) =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        bool ok = true;
+        uint32_t r[32];
+        for (int it = 0; it < n_main && ok; it++) {
+            const int s = it & 1;
+            ok = mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u, p.error_flag, 2);
+            if (!ok) break;
+            const uint8_t* rowp = smem + s * kStageBytes + row * 128;
+            #pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (row & 7)) << 4));
+                r[4 * c + 0] = __float_as_uint(v.x); r[4 * c + 1] = __float_as_uint(v.y);
+                r[4 * c + 2] = __float_as_uint(v.z); r[4 * c + 3] = __float_as_uint(v.w);
+            }
+            if (it >= 2) {      // the MMAs of iteration it - 2 read this TMEM slot
+                ok = mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u, p.error_flag, 5);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t slot = lane_base + kCol5Slots + 64u * (uint32_t)s;
+            if (!p.exact_main) {      // single pass: round to nearest TF32 (see version 4)
+                #pragma unroll
+                for (int i = 0; i < 32; i++) r[i] += 0x1000u;
+            }
+            tmem_st32(slot, r);
+            if (p.exact_main) {
+                #pragma unroll
+                for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
+                tmem_st32(slot + 32u, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+        }
+        if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- tap columns of this position -> shared memory (every MMA, hence every read of the stages, has completed)
+        float* col = reinterpret_cast<float*>(smem);
+        {
+            float* mine = col + row * kColStride6;
+            tmem_ld32(lane_base, r);
+            #pragma unroll
+            for (int i = 0; i < 32; i++) mine[i] = __uint_as_float(r[i]);
+            tmem_ld32(lane_base + 32u, r);
+            #pragma unroll
+            for (int i = 0; i < 32; i++) mine[32 + i] = __uint_as_float(r[i]);
+            tmem_ld32(lane_base + 64u, r);
+            #pragma unroll
+            for (int i = 0; i < 17; i++) mine[64 + i] = __uint_as_float(r[i]);
+        }
+        named_bar_sync(1, 128);
+        // ---- gather: one item = two horizontally adjacent pixels (s0, s0 + 1) of pixel block (qa, pb), row r
+        const int t = threadIdx.x - 64;
+        #pragma unroll 1
+        for (int item = t; item < 4 * kBlkY6 * 2 * kBlkX6; item += 128) {
+            const int ly = item / (2 * kBlkX6), pr = item - ly * (2 * kBlkX6);
+            const int qa = ly >> 2, rr = ly & 3;
+            const int pb = pr >> 1, s0 = (pr & 1) * 2;
+            const int oy = 4 * (q0 + qa) + rr - 2, ox = 4 * (p0 + pb) + s0 - 2;
+            if (!ok || oy < 0 || oy >= p.H || ox < 0 || ox >= p.W) continue;
+            float acc0 = 0.f, acc1 = 0.f;
+            #pragma unroll
+            for (int da = 0; da < 3; da++) {
+                const int ky = rr + 4 * da;
+                if (ky > 8) continue;
+                const float* rowc = col + ((qa + 2 - da) * 16 + pb + 2) * kColStride6 + ky * 9 + s0;
+                #pragma unroll
+                for (int db = 0; db < 3; db++) {
+                    const float* c = rowc - db * kColStride6 + 4 * db;      // position pb + 2 - db, tap kx = s0 + 4 db
+                    if (s0 + 4 * db <= 8) acc0 += c[0];
+                    if (s0 + 4 * db + 1 <= 8) acc1 += c[1];
+                }
+            }
+            const size_t at = ((size_t)img * p.H + oy) * p.W + ox;
+            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + at) = make_float2(acc0, acc1);
+            if (p.out_u8) {
+                uchar2 v;
+                v.x = (uint8_t)(int)rintf(fminf(fmaxf(acc0, 16.f), 235.f));
+                v.y = (uint8_t)(int)rintf(fminf(fmaxf(acc1, 16.f), 235.f));
+                *reinterpret_cast<uchar2*>(p.out_u8 + at) = v;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols5) : "memory");
     }
@@ -1886,8 +2109,8 @@ int umma_version()
     static int v = 0;
     if (!v) {
         const char* env = getenv("EAE_UMMA_VERSION");
-        v = env ? atoi(env) : 5;
-        if (v < 1 || v > 5) v = 5;
+        v = env ? atoi(env) : 6;
+        if (v < 1 || v > 6) v = 6;
     }
     return v;
 }
@@ -2263,6 +2486,46 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         }
         gemm_umma_kernel<false><<<grid, kUmmaThreads, Cfg<false>::kSmemBytes, st>>>(map_a, map_b_hi, map_b_lo, p);
     }
+    EAE_LAUNCH_OK();
+    return 0;
+}
+
+int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
+                          bool exact3x, cudaStream_t st)
+{
+    if (!n) return 0;
+    if (H % 4 != 0 || W % 4 != 0 || !w.hi || (exact3x && !w.lo)) { set_error("tconv9s4: bad arguments"); return EAE_ERR_ARGUMENT; }
+    if (!g_error_flag) {
+        EAE_CUDA_OK(cudaMalloc(&g_error_flag, 4));
+        EAE_CUDA_OK(cudaMemset(g_error_flag, 0, 4));
+    }
+    const int H1 = H / 4, W1 = W / 4;
+    UmmaParams6 q;
+    memset(&q, 0, sizeof q);
+    q.kchunks = kCout / kChunkK;
+    q.tiles_y = (H1 + 1 + kBlkY6 - 1) / kBlkY6;      // pixel blocks 0 .. H1 (the first and the last are half blocks)
+    q.tiles_x = (W1 + 1 + kBlkX6 - 1) / kBlkX6;
+    q.H = H; q.W = W;
+    q.out_u8 = out_u8; q.out_f32 = out_f32;
+    q.exact_main = exact3x ? 1 : 0;
+    q.error_flag = g_error_flag;
+    CUtensorMap map_a, map_b_hi, map_b_lo;
+    const uint64_t adims[5] = {(uint64_t)kCout, (uint64_t)W1, (uint64_t)H1, 1, n};
+    const uint32_t abox[5] = {kChunkK, 16, 8, 1, 1};
+    EAE_TRY(make_map(&map_a, in, 5, adims, abox));
+    const uint64_t bdims[3] = {(uint64_t)kCout, kCout, 1};      // [tap column (81 used)][Cin], K-major
+    const uint32_t bbox[3] = {kChunkK, 96, 1};
+    EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
+    EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
+    static bool attr6_done = false;
+    if (!attr6_done) {
+        EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes6));
+        EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma6_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr6_done = true;
+    }
+    const uint64_t grid = (uint64_t)n * (uint64_t)(q.tiles_x * q.tiles_y);
+    if (grid >= (1ull << 31)) { set_error("tconv9s4: batch too large"); return EAE_ERR_ARGUMENT; }
+    tconv9s4_umma6_kernel<<<(uint32_t)grid, kThreads5, kSmemBytes6, st>>>(map_a, map_b_hi, map_b_lo, q);
     EAE_LAUNCH_OK();
     return 0;
 }

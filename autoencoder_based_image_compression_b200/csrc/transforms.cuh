@@ -22,6 +22,10 @@ struct UmmaWeights {
 // gamma: K-major hi/lo of the GDN weights when plan.fuse != 0 (kernel version 2), else NULL.
 int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
                      cudaStream_t st);
+// The last layer in one launch (kernel version 6): conv2d_transpose k9 s4 of `in` [n, H/4, W/4, 128] through the
+// K-major tap matrix `w` ([128 tap columns, 81 used][128 in]) + the col2im gather + the BT.601 cast / float output.
+int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
+                          bool exact3x, cudaStream_t st);
 // 1: operands from shared memory, no fusion; 2: A in TMEM, GDN / IGDN fusable; 3 (default): 2 + 256 rows per CTA
 // and a coalesced epilogue (env EAE_UMMA_VERSION).
 int umma_version();

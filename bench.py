@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=24, help='images per GPU per step')
     ap.add_argument('--height', type=int, default=512)
     ap.add_argument('--width', type=int, default=768)
-    ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'tf32x3'), choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'mixed'), choices=['fp32', 'tf32x3', 'tf32', 'mixed'])
     ap.add_argument('--cpu-sample', type=int, default=0, help='images in the CPU sample (0 = one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--coder-lanes', type=int, default=1,
@@ -416,6 +416,7 @@ def run_gpu_arm(args):
     # GDN / IGDN always use the 3-way split; fp32 = CUDA cores (no MMAs).
     passes = {'tf32': {'gemm_conv': 1., 'gemm_tconv': 1., 'gemm_gdn': 3., 'gemm_thin': 1.},
               'tf32x3': {'gemm_conv': 3., 'gemm_tconv': 3., 'gemm_gdn': 3., 'gemm_thin': 2.5},
+              'mixed': {'gemm_conv': 3., 'gemm_tconv': 1., 'gemm_gdn': 3., 'gemm_thin': 1.5},
               'fp32': {'gemm_conv': 0., 'gemm_tconv': 0., 'gemm_gdn': 0., 'gemm_thin': 0.}}[args.math]
     executed = sum(GFLOP_PER_IMAGE[k]*passes[k] for k in GFLOP_PER_IMAGE)*scale*n*args.steps/gemm_ms if gemm_ms > 0 else 0.
     # DRAM bytes per launch of this kernel from the committed ncu capture of this workload

@@ -262,6 +262,8 @@ typedef struct eae_weights {
 #define EAE_MATH_FP32_SIMT 0 /* fp32 FFMA on CUDA cores (exact-fp32 parity mode, always available) */
 #define EAE_MATH_TF32X3 1    /* tcgen05 kind::tf32, hi/lo split of both operands, 3 MMAs, fp32 accumulate */
 #define EAE_MATH_TF32 2      /* tcgen05 kind::tf32, single pass (throughput mode; index mismatches reported) */
+#define EAE_MATH_MIXED 3     /* analysis transform (it decides the quantization indices) as EAE_MATH_TF32X3; synthesis
+                              * transform single pass TF32 with 3xTF32 IGDN norms (its bar is PSNR within 0.01 dB) */
 
 typedef struct eae_codec eae_codec_t;
 

@@ -145,3 +145,35 @@ def test_single_pass_tf32_is_close_but_not_exact(native):
     print('single-pass TF32: index agreement {:.6f} ({} mismatches of {})'.format(frac, nb, y.size))
     assert frac > 0.995
     assert numpy.abs(y - y64).max() < 5e-3*numpy.abs(y64).max()
+
+
+def test_mixed_mode_keeps_the_index_bar_and_the_psnr_bar(native):
+    """math='mixed': the analysis transform is the 3xTF32 one bit for bit (the indices, hence the bitstream, do not
+    change); the synthesis transform contracts in single-pass TF32 and is held to the north star's bar for
+    reconstructions: PSNR within 0.01 dB of the oracle's, no pixel off by more than one grey level."""
+    rng = numpy.random.default_rng(4)
+    w = visible_weights(0, False)
+    lum = util.synthetic_luma(rng, 2, 512, 768)[..., None]
+    mixed = native_codec.Codec(w, False, math='mixed')
+    exact = native_codec.Codec(w, False, math='tf32x3')
+    y = mixed.encode(lum)
+    assert numpy.array_equal(y, exact.encode(lum))
+    y32 = T.encoder(lum.astype(numpy.float32), w, False)
+    q = oracle_glue.quantize_per_map(y32, numpy.ones(128, dtype=numpy.float32))
+    want_f = T.decoder(q, w, False)
+    want = oracle_glue.cast_bt601(want_f)[..., 0]
+    assert want.std() > 5
+    rec_f = mixed.decode_float(q)
+    rel = numpy.abs(rec_f - want_f).max()/numpy.abs(want_f).max()
+    rec = mixed.decode(q)[..., 0]
+    delta = numpy.abs(rec.astype(numpy.int32) - want.astype(numpy.int32))
+    worst = 0.
+    for i in range(2):
+        psnr_gpu = oracle_glue.psnr_2d(lum[i, :, :, 0], rec[i])
+        psnr_ref = oracle_glue.psnr_2d(lum[i, :, :, 0], want[i])
+        worst = max(worst, abs(psnr_gpu - psnr_ref))
+    print('mixed mode: float reconstruction max rel err {:.2e}, uint8 mismatches {:.4f}, PSNR delta {:.5f} dB'.format(
+        rel, (delta != 0).mean(), worst))
+    assert worst < 0.01
+    assert delta.max() <= 1 and (delta != 0).mean() < 0.05
+    assert rel < 5e-3
