@@ -63,6 +63,7 @@ PROTOTYPES = {
     'eae_device_info': (c_int, [c_int, P(c_int), P(c_int), P(c_int), P(ctypes.c_size_t)]),
     'eae_launch_count': (u64, []),
     'eae_set_device': (c_int, [c_int]),
+    'eae_set_blocking_sync': (c_int, [c_int]),
     'eae_profile_enable': (c_int, [c_int]),
     'eae_profile_reset': (c_int, []),
     'eae_profile_read': (c_int, [c_int, P(u64), P(ctypes.c_double)]),
@@ -131,10 +132,11 @@ def lib():
     """Loads ``libeae_b200.so`` once. Raises ``RuntimeError`` when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.isfile(LIB_PATH):
+        path = os.environ.get('EAE_LIB_PATH') or LIB_PATH      # (experiments: a variant build of the same sources)
+        if not os.path.isfile(path):
             raise RuntimeError('{} is missing: run `python -m autoencoder_based_image_compression_b200.build` '
-                               '(or __graft_entry__.build()). There is no CPU fallback.'.format(LIB_PATH))
-        handle = ctypes.CDLL(LIB_PATH)
+                               '(or __graft_entry__.build()). There is no CPU fallback.'.format(path))
+        handle = ctypes.CDLL(path)
         for (name, (restype, argtypes)) in PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.restype = restype

@@ -487,6 +487,16 @@ __global__ void first_error_finish_kernel(uint32_t* key, uint32_t* flag1)
     *flag1 = *key == 0xFFFFFFFFu ? 0u : (*key & 0xFFu);
 }
 
+// (see prefer_max_shared in common.cuh)
+void codec_carveouts()
+{
+    static uint64_t seen = 0;
+    if (!first_use_on_device(&seen)) return;
+    prefer_max_shared(stream_offsets_kernel); prefer_max_shared(write_header_kernel); prefer_max_shared(pack_payload_kernel);
+    prefer_max_shared(batch_stats_kernel); prefer_max_shared(mailbox_kernel); prefer_max_shared(copy_prefix_kernel);
+    prefer_max_shared(first_error_kernel); prefer_max_shared(first_error_finish_kernel);
+}
+
 int ensure_mailbox(eae_codec* c)
 {
     if (c->mailbox) return 0;
@@ -530,6 +540,7 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
                       eae_batch_stats_t* stats_dev, cudaStream_t st)
 {
     EAE_TRY(check_dims(n, h, w));
+    codec_carveouts();
     EAE_TRY(upload_params(c, prm, st));
     const uint32_t L = prm->truncated_unary_length;
     const uint32_t hw3 = (h / 16) * (w / 16);
@@ -585,6 +596,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
                         uint32_t h, uint32_t w, uint8_t* rec_dev, cudaStream_t st)
 {
     EAE_TRY(check_dims(n, h, w));
+    codec_carveouts();
     EAE_TRY(upload_params(c, prm, st));
     const uint32_t L = prm->truncated_unary_length;
     const uint32_t hw3 = (h / 16) * (w / 16);

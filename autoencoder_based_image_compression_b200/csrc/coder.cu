@@ -631,6 +631,35 @@ size_t coder_encode_scratch_bytes(uint32_t n_streams, uint32_t size, uint32_t L)
     return ((size_t)n_streams * (uwords + 1) * 4 + 255) & ~(size_t)255;
 }
 
+// Debug (scripts/pipeline_probe.py): EAE_PROBE_SKIP bit 0 skips the binarisation launch, bit 1 the arithmetic
+// encoder, bit 2 the decoder - timing experiments only, the results are garbage.
+static int probe_skip()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EAE_PROBE_SKIP"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+// Threads per CTA of the one-thread-per-stream kernels (debug: EAE_CODER_BLOCK overrides).
+static uint32_t coder_block(uint64_t threads)
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EAE_CODER_BLOCK"); v = e ? atoi(e) : 0; }
+    if (v == 32 || v == 64 || v == 128 || v == 256) return (uint32_t)v;
+    return threads <= 148ull * 4ull * 32ull ? 32u : 64u;
+}
+
+// (see prefer_max_shared in common.cuh)
+static void coder_carveouts()
+{
+    static uint64_t seen = 0;
+    if (!first_use_on_device(&seen)) return;
+    prefer_max_shared(encode_streams_kernel); prefer_max_shared(decode_streams_kernel);
+    prefer_max_shared(encode_streams2_kernel); prefer_max_shared(decode_streams2_kernel);
+    prefer_max_shared(encode_streams3_kernel); prefer_max_shared(decode_streams3_kernel);
+    prefer_max_shared(binarize_streams_kernel);
+}
+
 int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_t size,
                           const double* table_dev, uint32_t table_rows, uint32_t L,
                           const uint8_t* skip_mask_dev, uint8_t* bac_slots, uint8_t* byp_slots,
@@ -639,6 +668,7 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
                           const uint8_t* row_flags_dev)
 {
     if (n_streams == 0) return 0;
+    coder_carveouts();
     if (coder_version() == 1) {
         const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
         encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
@@ -657,6 +687,7 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
     uint32_t* ubits = nbins + n_streams;
     const uint32_t warps = 4;
     const size_t smem = (size_t)warps * (L + 2u + 34u) * 4;
+    if (!(probe_skip() & 1))
     binarize_streams_kernel<<<ceil_div_u32(n_streams, warps), warps * 32, smem, st>>>(
         idx_planar, n_streams, size, table_rows, L, skip_mask_dev, nbins, ubits, uwords, byp_slots, slot_bytes,
         byp_bits);
@@ -664,7 +695,8 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
     const uint32_t lanes = lanes_v2(n_streams, lanes_req);
     const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
     const uint64_t threads = (uint64_t)n_streams * lanes;
-    const uint32_t block = threads <= 148ull * 4ull * 32ull ? 32u : 64u;   // few warps: one per CTA, spread over the SMs
+    const uint32_t block = coder_block(threads);   // few warps: one per CTA, spread over the SMs
+    if (probe_skip() & 2) { if (own) EAE_CUDA_OK(cudaFreeAsync(own, st)); return 0; }
     if (coder_version() == 2)
         encode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
             nbins, ubits, uwords, n_streams, table_dev, table_rows, L, skip_mask_dev, bac_slots, slot_bytes,
@@ -686,6 +718,7 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
                           const uint64_t* qtable_dev, const uint8_t* row_flags_dev)
 {
     if (n_streams == 0) return 0;
+    coder_carveouts();
     if (coder_version() == 1) {
         const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
         decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
@@ -697,7 +730,8 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
     const uint32_t lanes = lanes_v2(n_streams, lanes_req);
     const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
     const uint64_t threads = (uint64_t)n_streams * lanes;
-    const uint32_t block = threads <= 148ull * 4ull * 32ull ? 32u : 64u;
+    const uint32_t block = coder_block(threads);
+    if (probe_skip() & 4) return 0;
     if (coder_version() == 2)
         decode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
             idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off, bac_bits,

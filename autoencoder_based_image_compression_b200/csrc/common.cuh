@@ -78,6 +78,18 @@ struct ProfScope {
     cudaStream_t stream;
 };
 
+// The tensor kernels need (almost) the whole shared memory of an SM, i.e. the largest carveout. An SM whose resident
+// CTAs were launched under a smaller carveout cannot take such a CTA until it has drained and been reconfigured - and
+// the arithmetic coder's CTAs live for milliseconds. So every kernel that runs beside the tensor kernels in the
+// multi-stream pipeline asks for the same (maximum) carveout. first_use_on_device: true the first time it is called
+// with this mask on the current device.
+bool first_use_on_device(uint64_t* seen_mask);
+template <typename K> inline void prefer_max_shared(K kernel)
+{
+    cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+}
+
 // Returns 0 if a CUDA device is usable, EAE_ERR_CUDA (with message) otherwise.
 int require_device();
 

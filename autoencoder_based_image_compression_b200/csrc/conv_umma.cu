@@ -700,6 +700,11 @@ constexpr int kImgBoxW = 96, kImgBoxH = 69, kImgPadX = 14;
 constexpr int kImgBytes = ((kImgBoxW * kImgBoxH + 127) / 128) * 128;
 constexpr int kSmemBytes3 = kStages3 * kStageBytes3 + kImgBytes + 1024 + 256;
 constexpr int kUmmaThreads3 = 320;
+// Registers per thread of versions 3 and 4 (experiment knob): ten warps sit 3 / 3 / 2 / 2 on the four sub-partitions.
+#ifndef EAE_MAXREGS34
+#define EAE_MAXREGS34 128
+#endif
+constexpr int kMaxRegs34 = EAE_MAXREGS34;
 constexpr uint32_t kCol3Acc0 = 0, kCol3Acc1 = 128, kCol3Slots = 256, kCol3Nrm0 = 256, kCol3Nrm1 = 384;
 constexpr uint32_t kTmemBase0 = 0;      // TMEM address of a 512-column allocation on an otherwise empty SM
 
@@ -986,7 +991,7 @@ __device__ __forceinline__ bool gdn_tail_ts_run(const GdnTailTs& t, int set, int
     return ok;
 }
 
-__global__ void __launch_bounds__(kUmmaThreads3, 1)
+__global__ void __maxnreg__(kMaxRegs34)
 gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
                   const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ CUtensorMap map_img,
@@ -1289,7 +1294,7 @@ struct UmmaParams4 {
     UmmaGroup4 groups[kMaxGroups4];
 };
 
-__global__ void __launch_bounds__(kUmmaThreads3, 1)
+__global__ void __maxnreg__(kMaxRegs34)
 gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
                   const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4 p)

@@ -23,6 +23,16 @@ void set_error(const char* fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+bool first_use_on_device(uint64_t* seen_mask)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    const uint64_t bit = 1ull << (dev & 63);
+    if (*seen_mask & bit) return false;
+    *seen_mask |= bit;
+    return true;
+}
+
 int require_device()
 {
     int n = 0;
@@ -86,6 +96,13 @@ extern "C" int eae_set_device(int device)
 {
     EAE_TRY(require_device());
     EAE_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int eae_set_blocking_sync(int on)
+{
+    EAE_TRY(require_device());
+    EAE_CUDA_OK(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
     return 0;
 }
 

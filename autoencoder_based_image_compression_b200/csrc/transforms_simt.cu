@@ -305,10 +305,20 @@ int launch_col2im_k9s4(const float* P, uint8_t* out_u8, float* out_f32, uint32_t
     return 0;
 }
 
+// (see prefer_max_shared in common.cuh)
+static void glue_carveouts()
+{
+    static uint64_t seen = 0;
+    if (!first_use_on_device(&seen)) return;
+    prefer_max_shared(quantize_to_planar_kernel); prefer_max_shared(dequantize_from_planar_kernel);
+    prefer_max_shared(col2im_k9s4_kernel); prefer_max_shared(im2col_k9s4_kernel);
+}
+
 int launch_quantize_to_planar(const float* y, const float* mean, const float* delta, int16_t* idx_planar,
                               float* q_off, uint32_t n, uint32_t hw, uint32_t* flag, cudaStream_t st)
 {
     if (!n || !hw) return 0;
+    glue_carveouts();
     if (n > 65535u) { set_error("quantize: batch %u exceeds grid.y", n); return EAE_ERR_ARGUMENT; }
     quantize_to_planar_kernel<<<dim3(ceil_div_u32(hw, 32), n), 256, 0, st>>>(y, mean, delta, idx_planar,
                                                                             q_off, hw, flag);
@@ -320,6 +330,7 @@ int launch_dequantize_from_planar(const int16_t* idx_planar, const float* mean, 
                                   float* q_off, uint32_t n, uint32_t hw, cudaStream_t st)
 {
     if (!n || !hw) return 0;
+    glue_carveouts();
     if (n > 65535u) { set_error("dequantize: batch %u exceeds grid.y", n); return EAE_ERR_ARGUMENT; }
     dequantize_from_planar_kernel<<<dim3(ceil_div_u32(hw, 32), n), 256, 0, st>>>(idx_planar, mean, delta,
                                                                                 q_off, hw);

@@ -48,9 +48,12 @@ def parse_args():
     ap.add_argument('--math', default=os.environ.get('EAE_MATH', 'mixed'), choices=['fp32', 'tf32x3', 'tf32', 'mixed'])
     ap.add_argument('--cpu-sample', type=int, default=0, help='images in the CPU sample (0 = one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--blocking-sync', type=int, default=1,
+                    help='1: host threads sleep while they wait for the GPU (one thread per pipeline slot and one process '
+                         'per GPU would otherwise spin on more threads than the box has cores); 0: driver default')
     ap.add_argument('--coder-lanes', type=int, default=1,
                     help='GPU threads per coded stream (0 = one warp per stream: lowest latency)')
-    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '8')),
+    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '12')),
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')
     return ap.parse_args()
 
@@ -239,6 +242,8 @@ def run_gpu_arm(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     _native.check(lib.eae_set_device(local_rank))
+    if args.blocking_sync:
+        _native.check(lib.eae_set_blocking_sync(1))
 
     (n, h, w) = (args.batch, args.height, args.width)
     (table, map_mean) = load_tables()

@@ -63,6 +63,11 @@ uint64_t eae_launch_count(void);
 
 /* Selects the device used by the entry points that take no codec (coder / glue); codecs carry their own. */
 int eae_set_device(int device);
+/* How host threads wait for the current device in the _host entry points: 1 = sleep on an interrupt
+ * (cudaDeviceScheduleBlockingSync), 0 = the driver's default (spins while cores outnumber contexts). Several host
+ * threads per GPU and one process per GPU (the pipelined codec on an 8-GPU box) oversubscribe the cores when every
+ * waiting thread spins; a blocked thread costs a wake-up of some tens of microseconds per call instead. */
+int eae_set_blocking_sync(int on);
 
 /* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of
  * a class). Classes: 0 gemm_conv (k5 s2 convolutions), 1 gemm_tconv (k5 s2 transposed convolutions),
