@@ -245,7 +245,11 @@ int run_layer(eae_codec* c, GemmPlan* plans, int n_plans, int kind, const UmmaWe
     const bool fuse = gdn >= 0 && can_fuse(c, kind);
     const UmmaWeights gw{gdn >= 0 ? c->gk_hi[gdn].as<float>() : nullptr, gdn >= 0 ? c->gk_lo[gdn].as<float>() : nullptr, 1};
     for (int i = 0; i < n_plans; i++) {
-        if (fuse) { plans[i].fuse = inverse ? 2 : 1; plans[i].fuse_beta = c->beta[gdn].as<float>(); }
+        if (fuse) {
+            plans[i].fuse = inverse ? 2 : 1; plans[i].fuse_beta = c->beta[gdn].as<float>();
+            // mixed mode, synthesis side: the norm of a fused IGDN in one rounded-TF32 pass as well (its bar is the PSNR)
+            plans[i].fuse_single_pass = (c->math == EAE_MATH_MIXED && !c->exact_now) ? 1 : 0;
+        }
         EAE_TRY(run_gemm(c, plans[i], kind, uw, fuse ? &gw : nullptr, st));
     }
     if (gdn >= 0 && !fuse) EAE_TRY(run_gdn(c, plans[0].out, plans[0].out, out_pixels, gdn, inverse, st));

@@ -49,6 +49,7 @@ struct GemmPlan {
     int out_split;       // output stored parity-split: [n][(y&1)*2+(x&1)][Hout/2][Wout/2][128]
     int fuse;            // tensor path only: 0 none, 1 GDN, 2 IGDN applied to (acc + bias) before the store
     const float* fuse_beta;
+    int fuse_single_pass;    //   the fused norm contracts in single-pass TF32 (squares rounded to nearest) instead of 3xTF32
     const uint8_t* img_u8;   // tensor path only: the layer is the k9 s4 convolution of this uint8 image [n, img_H, img_W]
     int img_H, img_W;        //   (A rows are gathered from the pixels inside the kernel; `in` is not read)
     int n_taps;

@@ -366,6 +366,7 @@ struct UmmaParams2 {
     int mode;                // EpilogueMode of a standalone launch
     int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
     int exact_main;          // 3xTF32 for the main contraction
+    int exact_gdn;           // 3xTF32 for the fused norm (versions 3 and 4)
     int cluster;             // CTAs per cluster (1, 2 or 4): each loads 1/cluster of every B tile and multicasts it
     int n_tiles;             // real tiles; the grid is rounded up to a multiple of `cluster`
     int tile_w_log2;
@@ -834,17 +835,20 @@ __device__ __forceinline__ void store_half4(const OutGeom4& g, const uint8_t* st
 struct GdnTailTs {
     uint8_t* area;
     uint64_t* g_full;      // [4] gamma chunk kc landed (single use)
-    uint64_t* x_ready;     // [2] A slot k written (one arrival per conversion warp of set k)
-    uint64_t* x_free;      // [2] the MMAs that read slot k completed
+    uint64_t* x_ready;     // [4] A slot (set k, sub-slot u) = [2 k + u] written (one arrival per conversion warp of set k)
+    uint64_t* x_free;      // [4] the MMAs that read that slot completed
+                           //     (3xTF32: one {hi | lo} slot per set, u = 0. Single pass: the 32 lo columns are a second hi
+                           //      slot, so a set converts step j + 2 while the tensor pipe still reads step j)
     uint64_t* acc0_read;   // x_0 copied out of TMEM (8 arrivals: every conversion warp)
     uint64_t* acc_full;
     uint64_t* nrm0_full;
     uint64_t* nrm_full;
+    int exact;             // 1: 3xTF32 norm (hi / lo squares, hi / lo gamma); 0: single pass, squares rounded to nearest TF32
 };
 __device__ __forceinline__ void gdn_tail_ts_init(const GdnTailTs& t)
 {
     for (int s = 0; s < 4; s++) mbar_init(&t.g_full[s], 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
+    for (int s = 0; s < 4; s++) { mbar_init(&t.x_ready[s], 4); mbar_init(&t.x_free[s], 1); }
     mbar_init(t.acc0_read, 8);
     mbar_init(t.nrm0_full, 1);
 }
@@ -854,16 +858,18 @@ __device__ __forceinline__ void gdn_tail_ts_producer(const GdnTailTs& t, const C
     if (!mbar_wait(t.acc_full, 0, error_flag, 0)) return;      // gamma lands on the buffers of the main loop
     for (int kc = 0; kc < 4; kc++) {
         uint8_t* g = t.area + kc * 2 * kTileBytes;
-        mbar_expect_tx(&t.g_full[kc], 2 * kTileBytes);
+        mbar_expect_tx(&t.g_full[kc], (t.exact ? 2 : 1) * kTileBytes);
         tma_load_3d(g, map_g_hi, &t.g_full[kc], kc * kChunkK, 0, 0);
-        tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[kc], kc * kChunkK, 0, 0);
+        if (t.exact) tma_load_3d(g + kTileBytes, map_g_lo, &t.g_full[kc], kc * kChunkK, 0, 0);
     }
 }
 __device__ __forceinline__ void gdn_tail_ts_mma(const GdnTailTs& t, uint32_t* error_flag)
 {
     for (int j = 0; j < 8; j++) {
-        const int h = j >> 2, kc = j & 3, sl = j & 1;
-        bool ok = mbar_wait(&t.x_ready[sl], (uint32_t)(j >> 1) & 1u, error_flag, 1);
+        const int h = j >> 2, kc = j & 3, sl = j & 1, i = j >> 1;
+        const int u = t.exact ? 0 : (i & 1);                                 // sub-slot of set sl
+        const uint32_t par = t.exact ? (uint32_t)i & 1u : (uint32_t)(i >> 1) & 1u;
+        bool ok = mbar_wait(&t.x_ready[2 * sl + u], par, error_flag, 1);
         if (ok) ok = mbar_wait(&t.g_full[kc], 0, error_flag, 1);
         if (ok && j == 4) ok = mbar_wait(t.acc0_read, 0, error_flag, 1);
         if (!__all_sync(0xFFFFFFFFu, ok)) return;
@@ -871,15 +877,17 @@ __device__ __forceinline__ void gdn_tail_ts_mma(const GdnTailTs& t, uint32_t* er
         if (elect_one()) {
             const uint32_t g = smem_u32(t.area + kc * 2 * kTileBytes);
             const uint32_t d = kTmemBase0 + (h ? kCol3Acc0 : kCol3Nrm0);
-            const uint32_t a_hi = kTmemBase0 + kCol3Nrm1 + 64u * (uint32_t)sl, a_lo = a_hi + 32u;
+            const uint32_t a_hi = kTmemBase0 + kCol3Nrm1 + 64u * (uint32_t)sl + 32u * (uint32_t)u, a_lo = a_hi + 32u;
             #pragma unroll
             for (int k = 0; k < kChunkK / 8; k++) {
                 const uint64_t g_hi = make_desc(g + k * 32);
                 umma_tf32_ts(d, a_hi + 8 * k, g_hi, (kc == 0 && k == 0) ? 0u : 1u);
-                umma_tf32_ts(d, a_lo + 8 * k, g_hi, 1u);
-                umma_tf32_ts(d, a_hi + 8 * k, make_desc(g + kTileBytes + k * 32), 1u);
+                if (t.exact) {
+                    umma_tf32_ts(d, a_lo + 8 * k, g_hi, 1u);
+                    umma_tf32_ts(d, a_hi + 8 * k, make_desc(g + kTileBytes + k * 32), 1u);
+                }
             }
-            umma_commit(&t.x_free[sl]);
+            umma_commit(&t.x_free[2 * sl + u]);
             if (j == 3) umma_commit(t.nrm0_full);
             if (j == 7) umma_commit(t.nrm_full);
         }
@@ -897,12 +905,14 @@ __device__ __forceinline__ bool gdn_tail_ts_run(const GdnTailTs& t, int set, int
     bool ok = mbar_wait(t.acc_full, 0, error_flag, 3);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (stamp && threadIdx.x == 64) stamp[4] = clock64();
-    const uint32_t slot = lane_base + kCol3Nrm1 + 64u * (uint32_t)set;
     #pragma unroll
     for (int i = 0; i < 4 && ok; i++) {
         const int j = set + 2 * i, c0 = (j & 3) * kChunkK;
+        const int u = t.exact ? 0 : (i & 1);
+        const uint32_t slot = lane_base + kCol3Nrm1 + 64u * (uint32_t)set + 32u * (uint32_t)u;
         tmem_ld32_nowait(lane_base + ((j >> 2) ? kCol3Acc1 : kCol3Acc0) + c0, r);
-        if (i >= 1) ok = mbar_wait(&t.x_free[set], (uint32_t)(i - 1) & 1u, error_flag, 7);      // MMAs of step j - 2
+        // the MMAs that read this slot last: step j - 2 (3xTF32) or step j - 4 (single pass, second use of the sub-slot)
+        if (t.exact ? i >= 1 : i >= 2) ok = mbar_wait(&t.x_free[2 * set + u], t.exact ? (uint32_t)(i - 1) & 1u : 0u, error_flag, 7);
         tmem_ld_wait();
         if (!ok) break;
         if (i >= 1) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -917,14 +927,20 @@ __device__ __forceinline__ bool gdn_tail_ts_run(const GdnTailTs& t, int set, int
             r[4 * c] = __float_as_uint(x.x * x.x); r[4 * c + 1] = __float_as_uint(x.y * x.y);
             r[4 * c + 2] = __float_as_uint(x.z * x.z); r[4 * c + 3] = __float_as_uint(x.w * x.w);
         }
+        if (!t.exact) {               // single pass: round the squares to the nearest TF32 (see the main loop of version 4)
+            #pragma unroll
+            for (int q = 0; q < 32; q++) r[q] += 0x1000u;
+        }
         tmem_st32(slot, r);           // hi = the value itself (the tensor core truncates), lo = x^2 - trunc_tf32(x^2)
-        #pragma unroll
-        for (int q = 0; q < 32; q++) r[q] = __float_as_uint(__uint_as_float(r[q]) - __uint_as_float(r[q] & 0xFFFFE000u));
-        tmem_st32(slot + 32u, r);
+        if (t.exact) {
+            #pragma unroll
+            for (int q = 0; q < 32; q++) r[q] = __float_as_uint(__uint_as_float(r[q]) - __uint_as_float(r[q] & 0xFFFFE000u));
+            tmem_st32(slot + 32u, r);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t.x_ready[set]);
+        if (lane == 0) mbar_arrive(&t.x_ready[2 * set + u]);
         if (i == 1) {
             // x_0 = ACC0 + bias of this set's 64 channels -> staging of half 0; ACC0's columns then belong to NRM1
             #pragma unroll
@@ -1007,9 +1023,9 @@ gemm_umma3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint64_t* acc_full = bars + 3 * kStages3;
     uint64_t* nrm_full = bars + 3 * kStages3 + 1;
     uint64_t* img_full = bars + 3 * kStages3 + 2;
-    const GdnTailTs tail{smem, bars + 12 /* g_full[4] */, bars + 16 /* x_ready[2] */, bars + 18 /* x_free[2] */,
-                         bars + 20 /* acc0_read */, acc_full, bars + 21 /* nrm0_full */, nrm_full};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    const GdnTailTs tail{smem, bars + 12 /* g_full[4] */, bars + 16 /* x_ready[4] */, bars + 20 /* x_free[4] */,
+                         bars + 24 /* acc0_read */, acc_full, bars + 25 /* nrm0_full */, nrm_full, p.exact_gdn};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
@@ -1273,7 +1289,7 @@ constexpr int kUnionBytes = 41 * 1024;
 constexpr int kBStages4 = 4, kBStageBytes4 = 2 * kTileBytes;
 constexpr int kOffB4 = 2 * kUnionBytes;
 constexpr int kOffBars4 = kOffB4 + kBStages4 * kBStageBytes4;
-constexpr int kSmemBytes4 = kOffBars4 + 256 + 1024;
+constexpr int kSmemBytes4 = kOffBars4 + 512 + 1024;
 constexpr int kGdnStageBytes4 = 4 * kTileBytes;
 static_assert(3 * kGdnStageBytes4 <= kOffBars4, "GDN / epilogue stages must fit below the barriers");
 constexpr int kMaxGroups4 = 4;
@@ -1287,7 +1303,7 @@ struct UmmaParams4 {
     const float* bias;
     const float* beta;
     int Hout, Wout, out_mul, out_r, out_s, out_split;
-    int fuse, exact_main;
+    int fuse, exact_main, exact_gdn;
     long long* times;
     uint32_t* error_flag;
     UmmaTap4 taps[kMaxTaps];
@@ -1308,12 +1324,12 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                                            //     last tap of a group, its union buffer (a tcgen05.commit costs ~100 cycles of
                                            //     tensor-pipe time, three per iteration made the loop 15 % slower)
     uint64_t* u_full = bars + 8;           // [2] union box landed
-    uint64_t* split = bars + 12;           // [2] TMEM A slot written (128 arrivals: one conversion set)
+    uint64_t* split = bars + 12;           // [4] TMEM A slot of iteration it (it & 3) written (one arrival per conversion warp)
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
-    const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[2] */, bars + 24 /* x_free[2] */,
-                         bars + 26 /* acc0_read */, acc_full, bars + 27 /* nrm0_full */, nrm_full};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
+                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
@@ -1326,7 +1342,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&u_full[s], 1); mbar_init(&split[s], 4); }     // one arrival per conversion warp
+        for (int s = 0; s < 2; s++) mbar_init(&u_full[s], 1);
+        for (int s = 0; s < 4; s++) mbar_init(&split[s], 4);      // one arrival per conversion warp
         gdn_tail_ts_init(tail);
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
@@ -1394,14 +1411,16 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             bool ok = true;
             for (int it = 0; it < n_main && ok; it++) {
                 const int slot_i = it & 1, s = it & 3;
-                ok = mbar_wait(&split[slot_i], (uint32_t)(it >> 1) & 1u, p.error_flag, 1);
+                ok = mbar_wait(&split[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
                 if (ok) ok = mbar_wait(&b_full[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
                 ok = __all_sync(0xFFFFFFFFu, ok);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t st = smem_u32(smem + kOffB4 + s * kBStageBytes4);
-                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i;
+                    // single pass: the lo columns of a set's slot are a second hi slot (iterations it, it + 2 of the set)
+                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i +
+                                          (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
                     #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const uint32_t d = kTmemBase0 + (h ? kCol3Acc1 : kCol3Acc0);
@@ -1429,7 +1448,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         const int set = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t slot = lane_base + kCol3Slots + 128u * (uint32_t)set;
+        const uint32_t slot_set = lane_base + kCol3Slots + 128u * (uint32_t)set;
+        const int reuse = p.exact_main ? 2 : 4;      // the slot written now was read by the MMAs of iteration it - reuse
         const int row_in_union = (row >> 4) * kUnionW + (row & 15);     // half 1 adds 8 union rows
         bool ok = true;
         uint32_t r[32], hi[32];
@@ -1455,8 +1475,9 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                     dst[4 * c + 2] = __float_as_uint(v.z); dst[4 * c + 3] = __float_as_uint(v.w);
                 }
             }
-            if (it >= 2) {      // the MMAs of iteration it - 2 read this slot
-                ok = mbar_wait(&done[(it - 2) & 3], (uint32_t)((it - 2) >> 2) & 1u, p.error_flag, 5);
+            const uint32_t slot = slot_set + (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
+            if (it >= reuse) {
+                ok = mbar_wait(&done[(it - reuse) & 3], (uint32_t)((it - reuse) >> 2) & 1u, p.error_flag, 5);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
@@ -1481,7 +1502,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&split[set]);      // 4 arrivals instead of 128: the arrive chain is on the critical path
+            if (lane == 0) mbar_arrive(&split[it & 3]);   // 4 arrivals instead of 128: the arrive chain is on the critical path
         }
         const int wq = warp - 2;
         const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
@@ -2441,7 +2462,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.out = plan.out; q.bias = plan.bias; q.beta = plan.fuse_beta;
         q.Hout = plan.Hout; q.Wout = plan.Wout; q.out_mul = plan.out_mul; q.out_r = plan.out_r; q.out_s = plan.out_s;
         q.out_split = plan.out_split;
-        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0;
+        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0; q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
         q.error_flag = g_error_flag;
         // groups = input planes in use; taps sorted by group
         int fy_min[kMaxGroups4], fx_min[kMaxGroups4], fy_max[kMaxGroups4], fx_max[kMaxGroups4], group_of_plane[4] = {-1, -1, -1, -1};
@@ -2605,6 +2626,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.mode = p.mode;
         q.fuse = plan.fuse;
         q.exact_main = exact3x ? 1 : 0;
+        q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
         q.cluster = 1;
         q.error_flag = p.error_flag;
         memcpy(q.taps, p.taps, sizeof q.taps);
