@@ -351,7 +351,7 @@ __device__ __noinline__ uint32_t encode_bins_lean(const double* __restrict__ pro
     return e;
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 encode_streams3_kernel(const uint32_t* __restrict__ nbins, const uint32_t* __restrict__ ubits, uint32_t uwords,
                        uint32_t n_streams, const double* __restrict__ table, const uint64_t* __restrict__ qtable,
                        const uint8_t* __restrict__ row_flags, uint32_t table_rows, uint32_t L,
@@ -429,7 +429,7 @@ __device__ __forceinline__ void decode_prefixes_fast(const T* __restrict__ mrow,
     }
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 decode_streams3_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
                        const double* __restrict__ table, const uint64_t* __restrict__ qtable,
                        const uint8_t* __restrict__ row_flags, uint32_t table_rows, uint32_t L,

@@ -1,7 +1,9 @@
 """Per-layer table of the tap-list GEMM launches of one bench step from an ``ncu --set full`` capture.
 
     ncu -i gpurun_out/prof_rXX_gemm.ncu-rep --page raw --csv > raw.csv
-    python scripts/ncu_gemm_layers.py raw.csv "title" > profiles/rXX_ncu_full_gemm_layers.md
+    python scripts/ncu_gemm_layers.py raw.csv "title" [images] [math] > profiles/rXX_ncu_full_gemm_layers.md
+
+math = tf32x3 (3 MMAs per product everywhere) or mixed (synthesis side: one MMA per product, fused IGDN norms too).
 """
 import csv
 import sys
@@ -10,18 +12,23 @@ NAMES = ['conv1 k9 s4 (uint8 patches in-kernel) + GDN1', 'conv2 k5 s2 + GDN2', '
          'tconv1 phase (0,0), 4 taps + IGDN5', 'tconv1 phase (0,1), 6 taps + IGDN5', 'tconv1 phase (1,0), 6 taps + IGDN5',
          'tconv1 phase (1,1), 9 taps + IGDN5', 'tconv2 phase (0,0), 4 taps + IGDN6', 'tconv2 phase (0,1), 6 taps + IGDN6',
          'tconv2 phase (1,0), 6 taps + IGDN6', 'tconv2 phase (1,1), 9 taps + IGDN6',
-         'tconv3 k9 s4 (per-pixel tap matrix; col2im follows)']
+         'tconv3 k9 s4 + col2im gather + BT.601 cast (persistent)']
 # algorithmic GFLOP per image and MMA passes actually issued
 ALG = [0.5096 + 0.8053, 5.0332 + 0.2013, 1.2583 + 0.0503, 0.0503] + [1.2583*t/25 + 0.2013/4 for t in (4, 6, 6, 9)] + \
       [5.0332*t/25 + 0.8053/4 for t in (4, 6, 6, 9)] + [0.5096]
-EXE = [0.5096*2 + 0.8053*3, (5.0332 + 0.2013)*3, (1.2583 + 0.0503)*3, 0.0503*3] + \
-      [(1.2583*t/25 + 0.2013/4)*3 for t in (4, 6, 6, 9)] + [(5.0332*t/25 + 0.8053/4)*3 for t in (4, 6, 6, 9)] + [0.5096*3]
+EXE = {'tf32x3': [0.5096*2 + 0.8053*3, (5.0332 + 0.2013)*3, (1.2583 + 0.0503)*3, 0.0503*3] +
+                 [(1.2583*t/25 + 0.2013/4)*3 for t in (4, 6, 6, 9)] + [(5.0332*t/25 + 0.8053/4)*3 for t in (4, 6, 6, 9)] +
+                 [0.5096*3],
+       'mixed': [0.5096*2 + 0.8053*3, (5.0332 + 0.2013)*3, (1.2583 + 0.0503)*3, 0.0503*3] +
+                [(1.2583*t/25 + 0.2013/4) for t in (4, 6, 6, 9)] + [(5.0332*t/25 + 0.8053/4) for t in (4, 6, 6, 9)] +
+                [0.5096]}
 
 
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
     title = sys.argv[2] if len(sys.argv) > 2 else 'tap-list GEMM, every layer of one 24-image step'
     images = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+    exe = EXE[sys.argv[4] if len(sys.argv) > 4 else 'tf32x3']
     hdr = rows[0]
 
     def col(name):
@@ -35,7 +42,7 @@ def main():
                              'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'launch__registers_per_thread',
                              'launch__shared_mem_per_block_dynamic']}
     print('# ' + title + '\n')
-    print('Source: `ncu --set full --clock-control none --import-source on -k regex:gemm_umma -s 13 -c 13` around '
+    print('Source: `ncu --set full --clock-control none --import-source on -k "regex:gemm_umma|tconv9s4" -s 13 -c 13` around '
           '`python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline` on one B200, read with `ncu -i ... --page raw --csv` '
           '(`scripts/ncu_gemm_layers.py`). Durations under ncu are cold-cache and serialised (SM clock {} GHz in the capture); the '
           'bench line is the timing. One launch = one layer (or one output phase of a transposed convolution) over {} images of '
@@ -54,10 +61,11 @@ def main():
             active = '{:.1f} %'.format(100.*h/(4.*cy))
         except ValueError:
             active = 'n/a (counter not collected in this pass)'
-        kern = 'v4' if 'umma4' in r[c['Kernel Name']] else ('v5' if 'umma5' in r[c['Kernel Name']] else 'v3')
+        name = r[c['Kernel Name']]
+        kern = 'v7' if 'umma7' in name else ('v6' if 'umma6' in name else ('v4' if 'umma4' in name else ('v5' if 'umma5' in name else 'v3')))
         print('| {} | {} | {} | {:.1f} | {:.1f} | {:.1f} | {} | {:.0f} | {:.0f} |'.format(
-            NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, active, ALG[k]*images/d*1e3, EXE[k]*images/d*1e3))
-        tt += d; tr += rd; tw += wr; ta += ALG[k]*images; te += EXE[k]*images
+            NAMES[k], kern, r[c['launch__grid_size']], d, rd, wr, active, ALG[k]*images/d*1e3, exe[k]*images/d*1e3))
+        tt += d; tr += rd; tw += wr; ta += ALG[k]*images; te += exe[k]*images
     print('| **all 13 launches** | | | **{:.1f}** | **{:.1f}** | **{:.1f}** | | **{:.0f}** | **{:.0f}** |'.format(
         tt, tr, tw, ta/tt*1e3, te/tt*1e3))
     print()

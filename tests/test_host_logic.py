@@ -194,3 +194,66 @@ def test_statistics_argument_checks(tmp_path):
     with pytest.raises(ValueError):      # tools.py:652-653
         stats.jensen_shannon_divergence(numpy.array([0., 1.]), numpy.array([0.5, 0.5]))
     assert abs(stats.jensen_shannon_divergence(numpy.array([0.5, 0.5]), numpy.array([0.5, 0.5]))) < 1e-15
+
+
+def test_last_layer_tile_gather_covers_every_pixel_once_in_col2im_order():
+    """Index arithmetic of the fused last layer (csrc/conv_umma.cu, kernel versions 6 / 7), restated in numpy: a tile of
+    8 x 16 positions starting two positions before its first pixel block completes the 6 x 14 pixel blocks whose
+    contributing positions lie inside it; the per-pixel sum runs in col2im_k9s4_kernel's order (da, db ascending), so
+    the two paths must agree bit for bit - for sizes that are not multiples of the tile as well."""
+    rng = numpy.random.default_rng(7)
+    for (H1, W1) in ((4, 4), (8, 12), (13, 31)):
+        (H, W) = (4*H1, 4*W1)
+        P = rng.standard_normal((H1, W1, 81)).astype(numpy.float32)
+
+        def tap(a, b, ky, kx):
+            return P[a, b, ky*9 + kx] if 0 <= a < H1 and 0 <= b < W1 else numpy.float32(0.)
+
+        want = numpy.zeros((H, W), dtype=numpy.float32)        # col2im_k9s4_kernel (transforms_simt.cu)
+        for oy in range(H):
+            for ox in range(W):
+                acc = numpy.float32(0.)
+                (a_hi, b_hi) = ((oy + 2) >> 2, (ox + 2) >> 2)
+                for da in range(3):
+                    (a, ky) = (a_hi - da, oy + 2 - 4*(a_hi - da))
+                    if a < 0 or a >= H1 or ky > 8:
+                        continue
+                    for db in range(3):
+                        (b, kx) = (b_hi - db, ox + 2 - 4*(b_hi - db))
+                        if b < 0 or b >= W1 or kx > 8:
+                            continue
+                        acc = numpy.float32(acc + P[a, b, ky*9 + kx])
+                want[oy, ox] = acc
+        got = numpy.full((H, W), numpy.nan, dtype=numpy.float32)
+        written = numpy.zeros((H, W), dtype=numpy.int32)
+        (tiles_y, tiles_x) = ((H1 + 1 + 5)//6, (W1 + 1 + 13)//14)
+        for ty in range(tiles_y):
+            for tx in range(tiles_x):
+                (q0, p0) = (ty*6, tx*14)
+                (a0, b0) = (q0 - 2, p0 - 2)
+                col = numpy.zeros((8, 16, 81), dtype=numpy.float32)      # TMA zero-fills outside the input
+                for la in range(8):
+                    for lb in range(16):
+                        if 0 <= a0 + la < H1 and 0 <= b0 + lb < W1:
+                            col[la, lb] = P[a0 + la, b0 + lb]
+                for item in range(4*6*2*14):
+                    (ly, pr) = divmod(item, 28)
+                    (qa, rr) = (ly >> 2, ly & 3)
+                    (pb, s0) = (pr >> 1, (pr & 1)*2)
+                    (oy, ox) = (4*(q0 + qa) + rr - 2, 4*(p0 + pb) + s0 - 2)
+                    if oy < 0 or oy >= H or ox < 0 or ox >= W:
+                        continue
+                    acc = [numpy.float32(0.), numpy.float32(0.)]
+                    for da in range(3):
+                        ky = rr + 4*da
+                        if ky > 8:
+                            continue
+                        for db in range(3):
+                            for e in range(2):
+                                kx = s0 + 4*db + e
+                                if kx <= 8:
+                                    acc[e] = numpy.float32(acc[e] + col[qa + 2 - da, pb + 2 - db, ky*9 + kx])
+                    got[oy, ox:ox + 2] = acc
+                    written[oy, ox:ox + 2] += 1
+        assert (written == 1).all()
+        assert numpy.array_equal(got, want)
