@@ -22,7 +22,18 @@ struct eae_codec {
     uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
     int no_direct_conv1 = 0;   // debug: env EAE_NO_DIRECT_CONV1=1 keeps the im2col pass in front of layer 1
+    // The four output phases of a transposed convolution as ONE grid (env EAE_PHASE_MERGE=1): 40 us less per 24-image step
+    // when the transforms run alone (the phases of a tile share their input box in L2, six dependent launches disappear),
+    // but 3 % fewer images/s when 16 pipeline slots share the GPU (1.77 against 1.72 ms per step: a 2304-CTA grid keeps
+    // the other slots' small kernels waiting longer than four 576-CTA grids do), so it is off by default.
+    int no_phase_merge = 1;
     cudaStream_t own_stream = nullptr;
+    // Experiment (env EAE_CODER_PRIORITY=1 / 2, off by default): the lossless-coding kernels on a side stream of the
+    // greatest / least priority, forked from and joined to the caller's stream with events. Measured with 16 pipeline
+    // slots: 1.87 ms per step with the side stream at either priority against 1.78 ms without it.
+    cudaStream_t coder_stream = nullptr;
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;
+    int coder_priority = 0;
 
     // ---- weights (device) ----
     DevBuf w1m;            // [96][128]   im2col matrix of weights_1 (rows >= 81 are zero)
@@ -250,7 +261,15 @@ int run_layer(eae_codec* c, GemmPlan* plans, int n_plans, int kind, const UmmaWe
             // mixed mode, synthesis side: the norm of a fused IGDN in one rounded-TF32 pass as well (its bar is the PSNR)
             plans[i].fuse_single_pass = (c->math == EAE_MATH_MIXED && !c->exact_now) ? 1 : 0;
         }
-        EAE_TRY(run_gemm(c, plans[i], kind, uw, fuse ? &gw : nullptr, st));
+    }
+    const bool tensor = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kind) & 1);
+    if (n_plans > 1 && n_plans <= 4 && tensor && !c->no_phase_merge) {
+        // the output phases of a transposed convolution as one grid (kernel version 4)
+        static const int prof_of_kind[4] = {kProfGemmConv, kProfGemmTconv, kProfGemmGdn, kProfGemmThin};
+        ProfScope prof(prof_of_kind[kind], st);
+        EAE_TRY(launch_gemm_umma(plans[0], uw, fuse ? &gw : nullptr, c->exact_now, st, plans + 1, n_plans - 1));
+    } else {
+        for (int i = 0; i < n_plans; i++) EAE_TRY(run_gemm(c, plans[i], kind, uw, fuse ? &gw : nullptr, st));
     }
     if (gdn >= 0 && !fuse) EAE_TRY(run_gdn(c, plans[0].out, plans[0].out, out_pixels, gdn, inverse, st));
     return 0;
@@ -539,6 +558,33 @@ uint8_t* device_alias_of_pinned(const void* host)
     return reinterpret_cast<uint8_t*>(attr.devicePointer);
 }
 
+// Work enqueued on the returned stream starts after everything already enqueued on `st`.
+int fork_coder_stream(eae_codec* c, cudaStream_t st, cudaStream_t* out)
+{
+    *out = st;
+    if (!c->coder_priority) return 0;
+    if (!c->coder_stream) {
+        int least = 0, greatest = 0;
+        EAE_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        EAE_CUDA_OK(cudaStreamCreateWithPriority(&c->coder_stream, cudaStreamNonBlocking, c->coder_priority == 2 ? least : greatest));
+        EAE_CUDA_OK(cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+        EAE_CUDA_OK(cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming));
+    }
+    EAE_CUDA_OK(cudaEventRecord(c->fork_event, st));
+    EAE_CUDA_OK(cudaStreamWaitEvent(c->coder_stream, c->fork_event, 0));
+    *out = c->coder_stream;
+    return 0;
+}
+
+// Work enqueued on `st` from now on starts after everything enqueued on the coder stream.
+int join_coder_stream(eae_codec* c, cudaStream_t st, cudaStream_t cs)
+{
+    if (cs == st) return 0;
+    EAE_CUDA_OK(cudaEventRecord(c->join_event, cs));
+    EAE_CUDA_OK(cudaStreamWaitEvent(st, c->join_event, 0));
+    return 0;
+}
+
 int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* img_dev, uint32_t n,
                       uint32_t h, uint32_t w, uint8_t* container_dev, uint64_t cap, uint64_t* total_dev,
                       eae_batch_stats_t* stats_dev, cudaStream_t st)
@@ -564,36 +610,40 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
                                           nc, hw3, c->flag.as<uint32_t>(), st));
     }
     c->last_idx_elems = (uint64_t)n_streams * hw3;
+    cudaStream_t cs = st;
+    EAE_TRY(fork_coder_stream(c, st, &cs));
     {
-        ProfScope prof(kProfCoderEncode, st);
+        ProfScope prof(kProfCoderEncode, cs);
         EAE_TRY(launch_encode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
-                                      c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), st,
+                                      c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->err.as<uint32_t>(), cs,
                                       c->coder_lanes, c->enc_scratch.p, c->qtable.as<uint64_t>(),
                                       c->row_flags.as<uint8_t>()));
     }
-    ProfScope prof_pack(kProfPack, st);
-    stream_offsets_kernel<<<1, 1024, 0, st>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
+    {
+    ProfScope prof_pack(kProfPack, cs);
+    stream_offsets_kernel<<<1, 1024, 0, cs>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
                                               kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
                                               c->byp_off.as<uint64_t>(), total_dev);
     EAE_LAUNCH_OK();
-    write_header_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(container_dev, n, h, w, L,
+    write_header_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, cs>>>(container_dev, n, h, w, L,
                                                                      c->bac_bits.as<uint32_t>(),
                                                                      c->byp_bits.as<uint32_t>(), n_streams);
     EAE_LAUNCH_OK();
-    pack_payload_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, st>>>(
+    pack_payload_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, cs>>>(
         container_dev, cap, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
         c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->bac_off.as<uint64_t>(),
         c->byp_off.as<uint64_t>(), n_streams);
     EAE_LAUNCH_OK();
     eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
-    EAE_CUDA_OK(cudaMemsetAsync(sd, 0, sizeof(eae_batch_stats_t), st));
-    batch_stats_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(c->bac_bits.as<uint32_t>(),
+    EAE_CUDA_OK(cudaMemsetAsync(sd, 0, sizeof(eae_batch_stats_t), cs));
+    batch_stats_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, cs>>>(c->bac_bits.as<uint32_t>(),
                                                                     c->byp_bits.as<uint32_t>(),
                                                                     c->err.as<uint32_t>(), n_streams, sd,
                                                                     c->flag.as<uint32_t>());
     EAE_LAUNCH_OK();
-    return 0;
+    }
+    return join_coder_stream(c, st, cs);
 }
 
 int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* container_dev, uint32_t n,
@@ -609,22 +659,25 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
+    cudaStream_t cs = st;
+    EAE_TRY(fork_coder_stream(c, st, &cs));
     const uint32_t* tbl = reinterpret_cast<const uint32_t*>(container_dev + kHeaderBytes);
-    stream_offsets_kernel<<<1, 1024, 0, st>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
+    stream_offsets_kernel<<<1, 1024, 0, cs>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
                                               c->bac_off.as<uint64_t>(), c->byp_off.as<uint64_t>(),
                                               c->total_bytes.as<uint64_t>());
     EAE_LAUNCH_OK();
     // De-interleave the stream table into the bit-count arrays the decoder reads.
-    EAE_CUDA_OK(cudaMemcpy2DAsync(c->bac_bits.p, 4, tbl, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
-    EAE_CUDA_OK(cudaMemcpy2DAsync(c->byp_bits.p, 4, tbl + 1, 8, 4, n_streams, cudaMemcpyDeviceToDevice, st));
+    EAE_CUDA_OK(cudaMemcpy2DAsync(c->bac_bits.p, 4, tbl, 8, 4, n_streams, cudaMemcpyDeviceToDevice, cs));
+    EAE_CUDA_OK(cudaMemcpy2DAsync(c->byp_bits.p, 4, tbl + 1, 8, 4, n_streams, cudaMemcpyDeviceToDevice, cs));
     {
-        ProfScope prof_dec(kProfCoderDecode, st);
+        ProfScope prof_dec(kProfCoderDecode, cs);
         EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
                                       nullptr, container_dev, c->bac_off.as<uint64_t>(), c->bac_bits.as<uint32_t>(),
                                       container_dev, c->byp_off.as<uint64_t>(), c->byp_bits.as<uint32_t>(),
-                                      c->err.as<uint32_t>(), st, c->coder_lanes, c->qtable.as<uint64_t>(),
+                                      c->err.as<uint32_t>(), cs, c->coder_lanes, c->qtable.as<uint64_t>(),
                                       c->row_flags.as<uint8_t>()));
     }
+    EAE_TRY(join_coder_stream(c, st, cs));
     c->last_idx_elems = (uint64_t)n_streams * hw3;
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
         const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
@@ -741,6 +794,8 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
     if (const char* env = getenv("EAE_NO_FUSE")) c->no_fuse = atoi(env);
     if (const char* env = getenv("EAE_NO_DIRECT_CONV1")) c->no_direct_conv1 = atoi(env);
+    if (const char* env = getenv("EAE_PHASE_MERGE")) c->no_phase_merge = atoi(env) ? 0 : 1;
+    if (const char* env = getenv("EAE_CODER_PRIORITY")) c->coder_priority = atoi(env);
     *out = c.release();
     return 0;
 }
@@ -750,6 +805,9 @@ extern "C" int eae_codec_destroy(eae_codec_t* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->coder_stream) { cudaStreamSynchronize(c->coder_stream); cudaStreamDestroy(c->coder_stream); }
+    if (c->fork_event) cudaEventDestroy(c->fork_event);
+    if (c->join_event) cudaEventDestroy(c->join_event);
     delete c;
     return 0;
 }

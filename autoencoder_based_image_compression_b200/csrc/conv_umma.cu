@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -1310,11 +1311,22 @@ struct UmmaParams4 {
     UmmaGroup4 groups[kMaxGroups4];
 };
 
+// Up to four launches that read the same input through the same weight array (the four output phases of a transposed
+// convolution) run as ONE grid: CTA b works on tile b / n_phases of phase b % n_phases. The phases of a tile are neighbours
+// in the grid, so the input box they share is fetched from HBM once; and six dependent launches per step disappear
+// (beside other streams' kernels a dependent launch waits ~10 us).
+struct UmmaParams4x {
+    int n_phases, pad;
+    UmmaParams4 ph[4];
+};
+
 __global__ void __maxnreg__(kMaxRegs34)
 gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
-                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4 p)
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4x pp)
 {
+    const UmmaParams4& p = pp.ph[blockIdx.x % (unsigned)pp.n_phases];
+    const int tile_linear = (int)(blockIdx.x / (unsigned)pp.n_phases);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars4);
@@ -1332,12 +1344,19 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 8 : nullptr;
-    if (stamp && threadIdx.x == 64) stamp[0] = clock64();
+    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 12 : nullptr;      // [8] start ns, [9] end ns, [10] SM id
+    if (stamp && threadIdx.x == 64) {
+        stamp[0] = clock64();
+        uint32_t smid;
+        long long t;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamp[8] = t; stamp[10] = smid;
+    }
     // tile = 16 x 16 positions: half h covers rows [a0 + 8 h, + 8)
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
+    const int img = tile_linear / tiles_per_img;
+    const int trem = tile_linear - img * tiles_per_img;
     const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
 
     if (warp == 0 && lane == 0) {
@@ -1523,7 +1542,12 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (stamp && threadIdx.x == 64) stamp[7] = clock64();
+    if (stamp && threadIdx.x == 64) {
+        stamp[7] = clock64();
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamp[9] = t;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
     }
@@ -2389,9 +2413,10 @@ int umma_version()
 }
 
 int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
-                     cudaStream_t st)
+                     cudaStream_t st, const GemmPlan* more, int n_more)
 {
     if (plan.M == 0) return 0;
+    if (n_more > 3) { set_error("gemm_umma: at most four plans per launch"); return EAE_ERR_ARGUMENT; }
     if (plan.Cin % kChunkK != 0 || plan.n_taps < 1 || plan.n_taps > kMaxTaps || !w.hi || (exact3x && !w.lo)) {
         set_error("gemm_umma: bad plan (Cin %d, taps %d)", plan.Cin, plan.n_taps);
         return EAE_ERR_ARGUMENT;
@@ -2452,9 +2477,16 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         EAE_TRY(make_map(&map_a, plan.in, 5, adims, abox));
     }
     const uint32_t grid = n_img * (uint32_t)(p.tiles_x * p.tiles_y);
-    if (umma_version() >= 4 && plan.n_taps > 1 && plan.Hg > 1 && plan.Cin == 128 && !plan.img_u8) {
-        // ---- version 4: tap groups that share one input plane read their boxes from one union box ----
-        UmmaParams4 q;
+    // Builds the version-4 parameters of one plan; false if its taps do not fit the union boxes.
+    auto build4 = [&](const GemmPlan& plan, UmmaParams4& q) -> bool {
+        UmmaParams p;      // (shadows the outer one: taps of THIS plan)
+        for (int t = 0; t < plan.n_taps; t++) {
+            const int dy = plan.taps[t].dy, dx = plan.taps[t].dx;
+            UmmaTap& u = p.taps[t];
+            if (plan.in_split) { u.plane = (dy & 1) * 2 + (dx & 1); u.fy = (dy - (dy & 1)) / 2; u.fx = (dx - (dx & 1)) / 2; }
+            else { u.plane = 0; u.fy = dy; u.fx = dx; }
+            u.w_tap = (int)(plan.taps[t].w_off / ((uint32_t)plan.Cin * kCout));
+        }
         memset(&q, 0, sizeof q);
         q.n_taps = plan.n_taps; q.kchunks = plan.Cin / kChunkK;
         q.tiles_x = (plan.Wg + 15) / 16; q.tiles_y = (plan.Hg + 15) / 16;
@@ -2481,7 +2513,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         }
         bool fits = true;
         for (int g = 0; g < n_groups; g++) fits = fits && fy_max[g] - fy_min[g] <= kUnionH - 16 && fx_max[g] - fx_min[g] <= kUnionW - 16;
-        if (fits && plan.mode == kEpiBias) {
+        if (!fits || plan.mode != kEpiBias) return false;
+        {
             q.n_groups = n_groups;
             int nt = 0;
             for (int g = 0; g < n_groups; g++) {
@@ -2496,6 +2529,27 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 q.taps[nt - 1].last = 1;
                 q.groups[g].pad = nt - 1;      // index of the group's last tap in the sorted list
             }
+        }
+        return true;
+    };
+    auto eligible4 = [&](const GemmPlan& pl) {
+        return umma_version() >= 4 && pl.n_taps > 1 && pl.n_taps <= kMaxTaps && pl.Hg > 1 && pl.Cin == 128 && !pl.img_u8 &&
+               pl.in == plan.in && pl.Hg == plan.Hg && pl.Wg == plan.Wg && pl.in_split == plan.in_split && pl.M == plan.M &&
+               pl.fuse == plan.fuse && pl.fuse_single_pass == plan.fuse_single_pass;
+    };
+    UmmaParams4x qx;
+    memset(&qx, 0, sizeof qx);
+    bool all4 = eligible4(plan) && build4(plan, qx.ph[0]);
+    for (int i = 0; i < n_more && all4; i++) all4 = eligible4(more[i]) && build4(more[i], qx.ph[1 + i]);
+    if (n_more > 0 && !all4) {      // no common launch: one after the other
+        EAE_TRY(launch_gemm_umma(plan, w, gamma, exact3x, st, nullptr, 0));
+        for (int i = 0; i < n_more; i++) EAE_TRY(launch_gemm_umma(more[i], w, gamma, exact3x, st, nullptr, 0));
+        return 0;
+    }
+    if (all4) {
+        {
+            const UmmaParams4& q = qx.ph[0];
+            qx.n_phases = 1 + n_more;
             CUtensorMap map_u;
             const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
             const uint32_t ubox[5] = {kChunkK, (uint32_t)kUnionW, (uint32_t)kUnionH, 1, 1};
@@ -2515,29 +2569,55 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
                 attr4_done = true;
             }
-            const uint32_t grid4 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
+            const uint32_t grid4 = n_img * (uint32_t)(q.tiles_x * q.tiles_y) * (uint32_t)qx.n_phases;
             static int timing4 = -1;
             if (timing4 < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing4 = e ? atoi(e) : 0; }
-            long long* d_times = nullptr;
+            // (EAE_UMMA_TIMING=4: only this kernel, from a buffer that is allocated once - cudaMalloc / cudaFree wait for
+            //  every stream of the device, which defeats measurements beside kernels running on other streams)
+            static long long* d_times = nullptr;
+            static size_t d_times_cap = 0;
             if (timing4) {
-                EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid4 * 8 * sizeof(long long)));
-                EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * 8 * sizeof(long long), st));
-                q.times = d_times;
+                if (d_times_cap < grid4) {
+                    if (d_times) cudaFree(d_times);
+                    d_times_cap = grid4 > 8192 ? grid4 : 8192;
+                    EAE_CUDA_OK(cudaMalloc(&d_times, d_times_cap * 12 * sizeof(long long)));
+                }
+                EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * 12 * sizeof(long long), st));
+                for (int i = 0; i < qx.n_phases; i++) qx.ph[i].times = d_times;
             }
-            gemm_umma4_kernel<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q);
+            gemm_umma4_kernel<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
             EAE_LAUNCH_OK();
             if (timing4) {
-                std::vector<long long> h((size_t)grid4 * 8);
+                std::vector<long long> h((size_t)grid4 * 12);
                 EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
                 EAE_CUDA_OK(cudaStreamSynchronize(st));
-                cudaFree(d_times);
                 double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (uint32_t b = 0; b < grid4; b++)
-                    for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 8 + j] - h[(size_t)b * 8]);
+                    for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 12 + j] - h[(size_t)b * 12]);
+                std::vector<long long> dur(grid4);
+                for (uint32_t b = 0; b < grid4; b++) dur[b] = h[(size_t)b * 12 + 7] - h[(size_t)b * 12];
+                std::sort(dur.begin(), dur.end());
+                // which SMs ran the CTAs, and when (global timer): makespan against the busy time of the SMs
+                {
+                    int per_sm[256] = {0};
+                    long long t_min = h[8], t_max = h[9];
+                    double busy_ns = 0.;
+                    for (uint32_t b = 0; b < grid4; b++) {
+                        per_sm[h[(size_t)b * 12 + 10] & 255]++;
+                        if (h[(size_t)b * 12 + 8] < t_min) t_min = h[(size_t)b * 12 + 8];
+                        if (h[(size_t)b * 12 + 9] > t_max) t_max = h[(size_t)b * 12 + 9];
+                        busy_ns += (double)(h[(size_t)b * 12 + 9] - h[(size_t)b * 12 + 8]);
+                    }
+                    int used = 0, most = 0, least = 1 << 30;
+                    for (int i = 0; i < 256; i++) if (per_sm[i]) { used++; most = per_sm[i] > most ? per_sm[i] : most; least = per_sm[i] < least ? per_sm[i] : least; }
+                    fprintf(stderr, "umma4 grid %u: %d SMs used, %d..%d CTAs per SM, makespan %.1f us, CTA time summed / 148 = %.1f us\n",
+                            grid4, used, least, most, (double)(t_max - t_min) * 1e-3, busy_ns * 1e-3 / 148.);
+                }
                 fprintf(stderr, "umma4 taps %d groups %d fuse %d grid %u: setup %.0f first_union %.0f acc_seen %.0f nrm_seen %.0f "
-                                "staged %.0f end %.0f (avg cycles from CTA start, conversion warp 2)\n",
+                                "staged %.0f end %.0f (avg cycles from CTA start, conversion warp 2); CTA duration min %lld "
+                                "p10 %lld median %lld p90 %lld max %lld\n",
                         q.n_taps, q.n_groups, q.fuse, grid4, acc[1] / grid4, acc[2] / grid4, acc[4] / grid4, acc[5] / grid4,
-                        acc[6] / grid4, acc[7] / grid4);
+                        acc[6] / grid4, acc[7] / grid4, dur[0], dur[grid4 / 10], dur[grid4 / 2], dur[grid4 * 9 / 10], dur[grid4 - 1]);
             }
             return 0;
         }
@@ -2579,7 +2659,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             attr5_done = true;
         }
         const uint32_t grid5 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
-        if (getenv("EAE_UMMA_TIMING")) {
+        if (getenv("EAE_UMMA_TIMING") && atoi(getenv("EAE_UMMA_TIMING")) == 1) {
             // Debug: which SM ran each CTA and when; prints the largest number of CTAs alive at once on one SM.
             long long* d_times = nullptr;
             EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid5 * 3 * sizeof(long long)));
@@ -2652,7 +2732,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             attr3_done = true;
         }
         static int timing = -1;
-        if (timing < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing = e ? atoi(e) : 0; }
+        if (timing < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing = (e && atoi(e) == 1) ? 1 : 0; }
         if (timing) {
             // Debug: per-CTA phase stamps, averaged over the grid, printed to stderr (synchronises the stream).
             long long* d_times = nullptr;

@@ -1,5 +1,6 @@
 // Runtime plumbing of libeae_b200.so: last-error text, device checks, pinned/device memory, streams
 // and events for callers (ctypes) that have no CUDA binding of their own.
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -202,7 +203,14 @@ extern "C" int eae_stream_create(void** stream)
     if (!stream) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(require_device());
     cudaStream_t s;
-    EAE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    const char* pr = getenv("EAE_STREAM_PRIORITY");      // debug: "high" creates the streams at the greatest priority
+    if (pr && pr[0] == 'h') {
+        int least = 0, greatest = 0;
+        EAE_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        EAE_CUDA_OK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest));
+    } else {
+        EAE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
     *stream = (void*)s;
     return 0;
 }

@@ -20,8 +20,10 @@ struct UmmaWeights {
     int n_taps;
 };
 // gamma: K-major hi/lo of the GDN weights when plan.fuse != 0 (kernel version 2), else NULL.
+// more / n_more: up to three further plans over the same input and weight array (the other output phases of a transposed
+// convolution); kernel version 4 runs them with `plan` as ONE grid, otherwise they are launched one after the other.
 int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
-                     cudaStream_t st);
+                     cudaStream_t st, const GemmPlan* more = nullptr, int n_more = 0);
 // The last layer in one launch (kernel version 6): conv2d_transpose k9 s4 of `in` [n, H/4, W/4, 128] through the
 // K-major tap matrix `w` ([128 tap columns, 81 used][128 in]) + the col2im gather + the BT.601 cast / float output.
 int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,

@@ -39,8 +39,8 @@ L2_BYTES = 126 << 20
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=48)
-    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=96)
+    ap.add_argument('--warmup', type=int, default=16)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=24, help='images per GPU per step')
     ap.add_argument('--height', type=int, default=512)

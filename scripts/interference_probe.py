@@ -86,17 +86,17 @@ def main():
         t1.record()
     torch.cuda.synchronize()
     print('{} launch alone: {:.3f} ms'.format(which, t0.elapsed_time(t1)))
-    steps = 12
-    for K in (0, 1, 2, 4):
+    steps = int(os.environ.get('PROBE_STEPS', '12'))
+    for K in [int(k) for k in os.environ.get('PROBE_KS', '0,1,2,4').split(',')]:
+        print('--- K = {}'.format(K), file=sys.stderr, flush=True)
         torch.cuda.synchronize()
-        for r in range(14):
+        for r in range(int(os.environ.get('PROBE_BG', '14'))):      # all of the background first: it must outlast the transforms
             for k in range(K):
                 background(k)
-            if r == 1:      # the background is running: start the clock on the transforms' stream
-                _native.check(lib.eae_event_record(ev[0], codec.stream))
-                for _ in range(steps):
-                    transforms()
-                _native.check(lib.eae_event_record(ev[1], codec.stream))
+        _native.check(lib.eae_event_record(ev[0], codec.stream))
+        for _ in range(steps):
+            transforms()
+        _native.check(lib.eae_event_record(ev[1], codec.stream))
         ms = ctypes.c_float(0.)
         _native.check(lib.eae_event_elapsed_ms(ev[0], ev[1], ctypes.byref(ms)))
         torch.cuda.synchronize()

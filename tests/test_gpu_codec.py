@@ -15,6 +15,10 @@ from tests.test_gpu_transforms import PARITY_MODES, visible_weights
 
 pytestmark = pytest.mark.gpu
 
+# The codec-level bars (byte-identical bitstreams, >= 99.99 % identical indices, PSNR within 0.01 dB, rate within 0.1 %)
+# also hold for the bench's default arithmetic: 3xTF32 analysis, single-pass rounded-TF32 synthesis.
+CODEC_MODES = PARITY_MODES + ['mixed']
+
 
 def oracle_pipeline(lum, w, learned, params):
     """CPU restatement of reconstructing_eae_kodak.py:144-224 for one batch."""
@@ -27,7 +31,7 @@ def oracle_pipeline(lum, w, learned, params):
     return (y, idx, rec)
 
 
-@pytest.mark.parametrize('math', PARITY_MODES)
+@pytest.mark.parametrize('math', CODEC_MODES)
 @pytest.mark.parametrize('learned', [False, True])
 def test_round_trip_and_byte_identity(native, golden, learned, math):
     rng = numpy.random.default_rng(3)
@@ -81,7 +85,7 @@ def test_round_trip_and_byte_identity(native, golden, learned, math):
     assert abs(total - bits_ref) <= 1e-3*bits_ref
 
 
-@pytest.mark.parametrize('math', PARITY_MODES)
+@pytest.mark.parametrize('math', CODEC_MODES)
 def test_quantization_sweep(native, golden, math):
     """BASELINE config 3 at test scale: one EAE, bin widths delta x {1, 2, 4, 8}."""
     rng = numpy.random.default_rng(4)
@@ -103,6 +107,40 @@ def test_quantization_sweep(native, golden, math):
         rates.append(stats['total_bits'])
         psnrs.append(oracle_glue.psnr_2d(lum[0], rec[0]))
     assert rates == sorted(rates, reverse=True)       # coarser bins never cost more bits
+
+
+def test_4k_frame_through_the_whole_codec(native, golden):
+    """BASELINE config 5 at test scale: one 2160 x 3840 frame (latent 135 x 240, not a multiple of any tile; 128 streams
+    of 32 400 symbols) through compress -> container -> decompress in the bench's default arithmetic."""
+    rng = numpy.random.default_rng(6)
+    w = visible_weights(1, False)
+    (h, wd) = (2160, 3840)
+    lum = util.synthetic_luma(rng, 1, h, wd)
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'))
+    codec = native_codec.Codec(w, False, math='mixed')
+    (blob, stats) = codec.compress(lum, params, return_stats=True)
+    idx = codec.last_indices(1, h, wd).reshape(128, -1)
+    assert idx.shape[1] == 135*240
+    (info, streams) = native_codec.parse_container(blob)
+    assert (info['n'], info['h'], info['w']) == (1, h, wd)
+    total = 0
+    for s in range(0, 128, 7):          # every 7th stream byte for byte against the CPU coder
+        want = oracle_coder.encode_map(idx[s], params.table[s], 'port')
+        assert want[0] == 0 and (streams[s][0], streams[s][1]) == (want[2], want[4])
+        assert numpy.array_equal(streams[s][2], want[1]) and numpy.array_equal(streams[s][3], want[3])
+    for s in range(128):
+        total += streams[s][0] + streams[s][1]
+    assert stats['total_bits'] == total
+    y32 = T.encoder(lum[..., None].astype(numpy.float32), w, False)
+    idx_ref = numpy.round(y32).astype(numpy.int16).reshape(-1, 128).T
+    assert (idx != idx_ref).mean() <= 1e-4
+    rec = codec.decompress(blob, params)
+    assert numpy.array_equal(codec.last_indices(1, h, wd).reshape(128, -1), idx)       # the coder inverts exactly
+    q = idx.T.reshape(1, 135, 240, 128).astype(numpy.float32)
+    want_rec = oracle_glue.cast_bt601(T.decoder(q, w, False))[0, :, :, 0]
+    diff = numpy.abs(rec[0].astype(numpy.int32) - want_rec.astype(numpy.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-2
+    assert abs(oracle_glue.psnr_2d(lum[0], rec[0]) - oracle_glue.psnr_2d(lum[0], want_rec)) < 0.01
 
 
 def test_container_errors(native, golden):
