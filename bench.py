@@ -424,9 +424,11 @@ def run_gpu_arm(args):
               'mixed': {'gemm_conv': 3., 'gemm_tconv': 1., 'gemm_gdn': 2.05, 'gemm_thin': 1.5},   # fused IGDN5 / IGDN6 norms: one pass
               'fp32': {'gemm_conv': 0., 'gemm_tconv': 0., 'gemm_gdn': 0., 'gemm_thin': 0.}}[args.math]
     executed = sum(GFLOP_PER_IMAGE[k]*passes[k] for k in GFLOP_PER_IMAGE)*scale*n*args.steps/gemm_ms if gemm_ms > 0 else 0.
-    # DRAM bytes per launch of this kernel from the committed ncu capture of this workload
-    # (profiles/r01_ncu_full_gemm_layers_final.md: 13 launches per step, 1802 MB per 24-image step).
-    traffic = 1801.7e6/13.*(n/24.)*scale if args.math != 'fp32' else None
+    # DRAM bytes per launch of this kernel from the committed ncu captures of this workload
+    # (profiles/r01_ncu_full_gemm_layers_v13.md: 13 launches per step, 1573 MB per 24-image step in the mixed mode;
+    #  1593 MB with 3xTF32 everywhere).
+    traffic = {'mixed': 1573.3e6, 'fp32': None}.get(args.math, 1593.3e6)
+    traffic = traffic/13.*(n/24.)*scale if traffic else None
     line['roofline'] = {
         'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
         'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',
