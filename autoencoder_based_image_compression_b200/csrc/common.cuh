@@ -90,6 +90,9 @@ template <typename K> inline void prefer_max_shared(K kernel)
                          (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// Is the per-kernel-class device profile (eae_profile_enable) recording?
+bool profiling_enabled();
+
 // Returns 0 if a CUDA device is usable, EAE_ERR_CUDA (with message) otherwise.
 int require_device();
 

@@ -52,6 +52,7 @@ struct ProfEvent { cudaEvent_t a, b; int cls; };
 static std::mutex g_prof_mutex;
 static std::vector<ProfEvent> g_prof_events;
 static std::atomic<int> g_prof_on{0};
+bool profiling_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
 static uint64_t g_prof_launches[kProfCount];
 static double g_prof_ms[kProfCount];
 

@@ -143,6 +143,47 @@ def test_4k_frame_through_the_whole_codec(native, golden):
     assert abs(oracle_glue.psnr_2d(lum[0], rec[0]) - oracle_glue.psnr_2d(lum[0], want_rec)) < 0.01
 
 
+def test_repeated_steps_replay_a_graph_with_identical_results(native, golden):
+    """From its second use with the same buffers, a step of the device-resident entry points (eae_compress_dev /
+    eae_decompress_dev) is captured into a CUDA graph and replayed (csrc/codec.cu, run_as_step_graph): same bytes, same
+    pixels, same launch count as the host entry points, which launch directly; a new image or new coding parameters behind
+    the same pointers must show up in the replayed step."""
+    import ctypes
+    rng = numpy.random.default_rng(8)
+    w = visible_weights(2, False)
+    (n, h, wd) = (2, 128, 192)
+    images = [util.synthetic_luma(rng, n, h, wd) for _ in range(2)]
+    prms = [native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1')),
+            native_codec.CodingParams(2*numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '2'))]
+    lib = native.lib()
+    codec = native_codec.Codec(w, False, math='mixed', own_stream=True)
+    plain = native_codec.Codec(w, False, math='mixed')            # host entry points: no graphs
+    bound = int(lib.eae_container_bound(n, h, wd, 10))
+    dev = torch.device('cuda', 0)
+    d_img = torch.zeros((n, h, wd), dtype=torch.uint8, device=dev)
+    d_cont = torch.zeros(bound, dtype=torch.uint8, device=dev)
+    d_rec = torch.zeros((n, h, wd), dtype=torch.uint8, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_stats = torch.zeros(ctypes.sizeof(native.BatchStats), dtype=torch.uint8, device=dev)
+    launches = []
+    for (k, (i, j)) in enumerate([(0, 0)]*5 + [(1, 0), (1, 1), (0, 1), (0, 0)]):
+        d_img.copy_(torch.from_numpy(images[i]))
+        torch.cuda.synchronize()
+        prm = prms[j].native()
+        before = lib.eae_launch_count()
+        native.check(lib.eae_compress_dev(codec.handle, ctypes.byref(prm), d_img.data_ptr(), n, h, wd, d_cont.data_ptr(), bound,
+                                          d_total.data_ptr(), d_stats.data_ptr(), codec.stream))
+        native.check(lib.eae_decompress_dev(codec.handle, ctypes.byref(prm), d_cont.data_ptr(), n, h, wd, d_rec.data_ptr(),
+                                            codec.stream))
+        native.check(lib.eae_stream_synchronize(codec.stream))
+        launches.append(lib.eae_launch_count() - before)
+        want = numpy.array(plain.compress(images[i], prms[j]), copy=True)
+        size = int(d_total.cpu()[0])
+        assert size == want.size and numpy.array_equal(d_cont.cpu().numpy()[:size], want), (k, i, j)
+        assert numpy.array_equal(d_rec.cpu().numpy(), plain.decompress(want, prms[j])), (k, i, j)
+    assert len(set(launches[1:5])) == 1, launches      # direct, captured and replayed steps count the same launches
+
+
 def test_container_errors(native, golden):
     w = wts.random_init(0, True)
     codec = native_codec.Codec(w, True)
