@@ -42,11 +42,13 @@ struct eae_codec {
     uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
     int no_direct_conv1 = 0;   // debug: env EAE_NO_DIRECT_CONV1=1 keeps the im2col pass in front of layer 1
-    // The four output phases of a transposed convolution as ONE grid (env EAE_PHASE_MERGE=1): 40 us less per 24-image step
-    // when the transforms run alone (the phases of a tile share their input box in L2, six dependent launches disappear),
-    // but 3 % fewer images/s when 16 pipeline slots share the GPU (1.77 against 1.72 ms per step: a 2304-CTA grid keeps
-    // the other slots' small kernels waiting longer than four 576-CTA grids do), so it is off by default.
-    int no_phase_merge = 1;
+    // The four output phases of a transposed convolution as ONE grid: 40 us less per 24-image step when the transforms run
+    // alone (the phases of a tile share their input box in L2, six dependent launches disappear). With 16 pipeline slots it
+    // wins 1.6 % when the step is replayed as a graph (1.59 vs 1.615 ms per step) and loses 3 % when it is launched kernel
+    // by kernel (1.77 vs 1.72 ms: a 2304-CTA grid keeps the other slots' small kernels waiting longer than four 576-CTA
+    // grids do). phase_merge: -1 = where the step runs as a graph (default), 0 = never, 1 = always (env EAE_PHASE_MERGE).
+    int phase_merge = -1;
+    int no_phase_merge = 1;    // the decision for the call being served
     cudaStream_t own_stream = nullptr;
     // Experiment (env EAE_CODER_PRIORITY=1 / 2, off by default): the lossless-coding kernels on a side stream of the
     // greatest / least priority, forked from and joined to the caller's stream with events. Measured with 16 pipeline
@@ -706,6 +708,7 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
     if (cap < kHeaderBytes + 8ull * n_streams) { set_error("container capacity too small"); return EAE_ERR_ARGUMENT; }
+    c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
     // parts: as encode_chunk's (1 = layer 1 has already been launched)
     auto body = [&](cudaStream_t st, int parts) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
@@ -775,6 +778,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     const uint32_t chunk = chunk_images(h, w);
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
+    c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
     auto body = [&](cudaStream_t st) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
     cudaStream_t cs = st;
@@ -915,7 +919,7 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
     if (const char* env = getenv("EAE_NO_FUSE")) c->no_fuse = atoi(env);
     if (const char* env = getenv("EAE_NO_DIRECT_CONV1")) c->no_direct_conv1 = atoi(env);
-    if (const char* env = getenv("EAE_PHASE_MERGE")) c->no_phase_merge = atoi(env) ? 0 : 1;
+    if (const char* env = getenv("EAE_PHASE_MERGE")) c->phase_merge = atoi(env);
     if (const char* env = getenv("EAE_CODER_PRIORITY")) c->coder_priority = atoi(env);
     if (const char* env = getenv("EAE_GRAPHS")) c->use_graphs = atoi(env);
     *out = c.release();
@@ -959,6 +963,7 @@ extern "C" int eae_codec_get_math(const eae_codec_t* c) { return c ? c->math : E
 extern "C" int eae_encode_dev(eae_codec_t* c, const uint8_t* img_dev, uint32_t n, uint32_t h, uint32_t w,
                               float* y_dev, void* stream)
 {
+    if (c) c->no_phase_merge = c->phase_merge == 1 ? 0 : 1;      // launched kernel by kernel
     if (!c || !img_dev || !y_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(check_dims(n, h, w));
     EAE_CUDA_OK(cudaSetDevice(c->device));
@@ -976,6 +981,7 @@ extern "C" int eae_encode_dev(eae_codec_t* c, const uint8_t* img_dev, uint32_t n
 extern "C" int eae_decode_dev(eae_codec_t* c, const float* q_dev, uint32_t n, uint32_t h, uint32_t w,
                               uint8_t* rec_dev, void* stream)
 {
+    if (c) c->no_phase_merge = c->phase_merge == 1 ? 0 : 1;      // launched kernel by kernel
     if (!c || !q_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(check_dims(n, h, w));
     EAE_CUDA_OK(cudaSetDevice(c->device));
@@ -1031,6 +1037,7 @@ extern "C" int eae_decode_host(eae_codec_t* c, const float* q, uint32_t n, uint3
 extern "C" int eae_decode_float_host(eae_codec_t* c, const float* q, uint32_t n, uint32_t h, uint32_t w,
                                      float* rec_out, void* stream)
 {
+    if (c) c->no_phase_merge = c->phase_merge == 1 ? 0 : 1;      // launched kernel by kernel
     if (!c || !q || !rec_out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_TRY(check_dims(n, h, w));
     EAE_CUDA_OK(cudaSetDevice(c->device));
