@@ -411,23 +411,54 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
 }
 
 // ---- container kernels -------------------------------------------------------------------------
-// Exclusive scan of per-stream byte sizes -> payload offsets. Single CTA, 1024 threads.
+// Exclusive scan of per-stream byte sizes -> payload offsets. Single CTA, 1024 threads. The same pass over the stream
+// table also does what used to be three more launches and two strided copies per step:
+//   compress   (header != NULL): container header + stream table, per-map bit totals / total bits / dead maps of the
+//                                batch (eae_batch_stats_t, no memset needed), first coder error -> flag[1]
+//   decompress (bac_out != NULL): de-interleaves the container's stream table into the bit-count arrays the decoder reads
+static_assert(1024 % EAE_NB_MAPS == 0, "stream_offsets_kernel: a thread must always see the same map");
+struct OffsetsExtra {
+    uint32_t* header;            // container as uint32 words, or NULL
+    uint32_t n, h, w, L;
+    eae_batch_stats_t* stats;    // or NULL
+    const uint32_t* err;         // per-stream coder error codes (with stats)
+    uint32_t* flag;              // flag[1] = an error code if any stream failed
+    uint32_t* bac_out;           // or NULL
+    uint32_t* byp_out;
+};
+
 __global__ void __launch_bounds__(1024)
 stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
                       uint32_t bits_stride, uint32_t n, uint64_t base, uint64_t* __restrict__ bac_off,
-                      uint64_t* __restrict__ byp_off, uint64_t* __restrict__ total_out)
+                      uint64_t* __restrict__ byp_off, uint64_t* __restrict__ total_out, const OffsetsExtra x)
 {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t running;
-    if (threadIdx.x == 0) running = base;
+    __shared__ unsigned long long red[1024];
+    __shared__ uint32_t red_dead[1024];
+    __shared__ uint32_t first_err;
+    if (threadIdx.x == 0) { running = base; first_err = 0; }
+    // stream s = start + thread with start a multiple of 1024 = 8 x 128: a thread always sees the same map (s % 128), so
+    // the per-map totals accumulate in registers and meet once at the end (no atomics on the way)
+    unsigned long long my_bits = 0;
+    uint32_t my_dead = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint32_t start = 0; start < n; start += 1024) {
         const uint32_t s = start + threadIdx.x;
         uint64_t nb = 0, nr = 0;
         if (s < n) {
-            nb = (bac_bits[(size_t)s * bits_stride] + 7u) >> 3;
-            nr = (byp_bits[(size_t)s * bits_stride] + 7u) >> 3;
+            const uint32_t bb = bac_bits[(size_t)s * bits_stride], rb = byp_bits[(size_t)s * bits_stride];
+            nb = (bb + 7u) >> 3;
+            nr = (rb + 7u) >> 3;
+            if (x.header) { x.header[8 + 2 * (size_t)s] = bb; x.header[8 + 2 * (size_t)s + 1] = rb; }
+            if (x.bac_out) { x.bac_out[s] = bb; x.byp_out[s] = rb; }
+            if (x.stats) {
+                my_bits += (unsigned long long)bb + rb;
+                // A map is dead (tools.py:294-320) iff all its symbols are 0 iff no sign bit was written.
+                my_dead += rb == 0 ? 1u : 0u;
+                if (x.err[s]) atomicCAS(&first_err, 0u, x.err[s]);      // (rare)
+            }
         }
         uint64_t v = nb + nr;
         for (int o = 1; o < 32; o <<= 1) {
@@ -452,21 +483,33 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
         if (threadIdx.x == 1023) running += incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = running;
-}
-
-__global__ void write_header_kernel(uint8_t* __restrict__ container, uint32_t n, uint32_t h, uint32_t w,
-                                    uint32_t L, const uint32_t* __restrict__ bac_bits,
-                                    const uint32_t* __restrict__ byp_bits, uint32_t n_streams)
-{
-    uint32_t* c32 = reinterpret_cast<uint32_t*>(container);
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) {
-        c32[0] = kMagic; c32[1] = kVersion; c32[2] = n; c32[3] = h; c32[4] = w; c32[5] = EAE_NB_MAPS; c32[6] = L; c32[7] = 0;
+    if (threadIdx.x == 0) {
+        *total_out = running;
+        if (x.header) {
+            x.header[0] = kMagic; x.header[1] = kVersion; x.header[2] = x.n; x.header[3] = x.h; x.header[4] = x.w;
+            x.header[5] = EAE_NB_MAPS; x.header[6] = x.L; x.header[7] = 0;
+        }
     }
-    if (s < n_streams) {
-        c32[8 + 2 * (size_t)s] = bac_bits[s];
-        c32[8 + 2 * (size_t)s + 1] = byp_bits[s];
+    if (x.stats) {
+        red[threadIdx.x] = my_bits;
+        red_dead[threadIdx.x] = my_dead;
+        __syncthreads();
+        if (threadIdx.x < EAE_NB_MAPS) {
+            unsigned long long bits = 0;
+            uint32_t dead = 0;
+            for (int k = 0; k < 1024 / EAE_NB_MAPS; k++) { bits += red[threadIdx.x + k * EAE_NB_MAPS]; dead += red_dead[threadIdx.x + k * EAE_NB_MAPS]; }
+            x.stats->bits_per_map[threadIdx.x] = bits;
+            red[threadIdx.x] = bits;
+            red_dead[threadIdx.x] = dead;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long total = 0, dead = 0;
+            for (int m = 0; m < EAE_NB_MAPS; m++) { total += red[m]; dead += red_dead[m]; }
+            x.stats->total_bits = total;
+            x.stats->nb_dead_maps = dead;
+            if (first_err) atomicCAS(x.flag + 1, 0u, first_err);      // first stream error wins
+        }
     }
 }
 
@@ -487,20 +530,6 @@ pack_payload_kernel(uint8_t* __restrict__ container, uint64_t cap, const uint8_t
     const uint8_t* sr = byp_slots + (size_t)s * slot_bytes;
     for (uint32_t i = lane; i < nb; i += 32) container[ob + i] = sb[i];
     for (uint32_t i = lane; i < nr; i += 32) container[orr + i] = sr[i];
-}
-
-__global__ void batch_stats_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
-                                   const uint32_t* __restrict__ err, uint32_t n_streams,
-                                   eae_batch_stats_t* __restrict__ stats, uint32_t* __restrict__ flag)
-{
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    const unsigned long long bits = (unsigned long long)bac_bits[s] + byp_bits[s];
-    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bits_per_map[s % EAE_NB_MAPS]), bits);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&stats->total_bits), bits);
-    // A map is dead (tools.py:294-320) iff all its symbols are 0 iff no sign bit was written.
-    if (byp_bits[s] == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->nb_dead_maps), 1ull);
-    if (err[s]) atomicCAS(flag + 1, 0u, err[s]);   // first stream error wins
 }
 
 // Everything a _host entry point needs to know about the batch, written straight into pinned host memory.
@@ -549,8 +578,8 @@ void codec_carveouts()
 {
     static uint64_t seen = 0;
     if (!first_use_on_device(&seen)) return;
-    prefer_max_shared(stream_offsets_kernel); prefer_max_shared(write_header_kernel); prefer_max_shared(pack_payload_kernel);
-    prefer_max_shared(batch_stats_kernel); prefer_max_shared(mailbox_kernel); prefer_max_shared(copy_prefix_kernel);
+    prefer_max_shared(stream_offsets_kernel); prefer_max_shared(pack_payload_kernel);
+    prefer_max_shared(mailbox_kernel); prefer_max_shared(copy_prefix_kernel);
     prefer_max_shared(first_error_kernel); prefer_max_shared(first_error_finish_kernel);
 }
 
@@ -734,25 +763,17 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     }
     {
     ProfScope prof_pack(kProfPack, cs);
+    eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
+    const OffsetsExtra extra{reinterpret_cast<uint32_t*>(container_dev), n, h, w, L, sd, c->err.as<uint32_t>(),
+                             c->flag.as<uint32_t>(), nullptr, nullptr};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
                                               kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
-                                              c->byp_off.as<uint64_t>(), total_dev);
-    EAE_LAUNCH_OK();
-    write_header_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, cs>>>(container_dev, n, h, w, L,
-                                                                     c->bac_bits.as<uint32_t>(),
-                                                                     c->byp_bits.as<uint32_t>(), n_streams);
+                                              c->byp_off.as<uint64_t>(), total_dev, extra);
     EAE_LAUNCH_OK();
     pack_payload_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, cs>>>(
         container_dev, cap, c->bac_slots.as<uint8_t>(), c->byp_slots.as<uint8_t>(), c->cw_slot,
         c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), c->bac_off.as<uint64_t>(),
         c->byp_off.as<uint64_t>(), n_streams);
-    EAE_LAUNCH_OK();
-    eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
-    EAE_CUDA_OK(cudaMemsetAsync(sd, 0, sizeof(eae_batch_stats_t), cs));
-    batch_stats_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, cs>>>(c->bac_bits.as<uint32_t>(),
-                                                                    c->byp_bits.as<uint32_t>(),
-                                                                    c->err.as<uint32_t>(), n_streams, sd,
-                                                                    c->flag.as<uint32_t>());
     EAE_LAUNCH_OK();
     }
     return join_coder_stream(c, st, cs);
@@ -784,13 +805,12 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     cudaStream_t cs = st;
     EAE_TRY(fork_coder_stream(c, st, &cs));
     const uint32_t* tbl = reinterpret_cast<const uint32_t*>(container_dev + kHeaderBytes);
+    // payload offsets, and the stream table de-interleaved into the bit-count arrays the decoder reads
+    const OffsetsExtra extra{nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>()};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
                                               c->bac_off.as<uint64_t>(), c->byp_off.as<uint64_t>(),
-                                              c->total_bytes.as<uint64_t>());
+                                              c->total_bytes.as<uint64_t>(), extra);
     EAE_LAUNCH_OK();
-    // De-interleave the stream table into the bit-count arrays the decoder reads.
-    EAE_CUDA_OK(cudaMemcpy2DAsync(c->bac_bits.p, 4, tbl, 8, 4, n_streams, cudaMemcpyDeviceToDevice, cs));
-    EAE_CUDA_OK(cudaMemcpy2DAsync(c->byp_bits.p, 4, tbl + 1, 8, 4, n_streams, cudaMemcpyDeviceToDevice, cs));
     {
         ProfScope prof_dec(kProfCoderDecode, cs);
         EAE_TRY(launch_decode_streams(c->idx_planar.as<int16_t>(), n_streams, hw3, c->table.as<double>(), EAE_NB_MAPS, L,
