@@ -112,6 +112,10 @@ uint32_t chunk_images(uint32_t h, uint32_t w)
     uint64_t n = (6ull << 30) / per_image;
     if (n < 1) n = 1;
     if (n > 256) n = 256;
+    if (const char* env = getenv("EAE_CHUNK_IMAGES")) {      // tests: exercise the multi-chunk path on small batches
+        const long v = atol(env);
+        if (v >= 1 && (uint64_t)v < n) n = (uint64_t)v;
+    }
     return (uint32_t)n;
 }
 

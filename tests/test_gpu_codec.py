@@ -184,6 +184,24 @@ def test_repeated_steps_replay_a_graph_with_identical_results(native, golden):
     assert len(set(launches[1:5])) == 1, launches      # direct, captured and replayed steps count the same launches
 
 
+def test_batches_larger_than_the_workspace_chunk(native, golden, monkeypatch):
+    """BASELINE config 4 shape at test scale: a batch that does not fit the activation workspace is transformed in chunks
+    (csrc/codec.cu, chunk_images) while the coder sees all its streams at once; the container must not depend on the
+    chunking. EAE_CHUNK_IMAGES shrinks the chunk so that 5 images take three passes (2 + 2 + 1)."""
+    rng = numpy.random.default_rng(9)
+    w = visible_weights(3, False)
+    lum = util.synthetic_luma(rng, 5, 64, 96)
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'))
+    whole = native_codec.Codec(w, False, math='mixed')
+    blob = numpy.array(whole.compress(lum, params), copy=True)
+    rec = numpy.array(whole.decompress(blob, params), copy=True)
+    monkeypatch.setenv('EAE_CHUNK_IMAGES', '2')
+    chunked = native_codec.Codec(w, False, math='mixed')
+    assert numpy.array_equal(chunked.compress(lum, params), blob)
+    assert numpy.array_equal(chunked.decompress(blob, params), rec)
+    assert numpy.array_equal(chunked.encode(lum[..., None]), whole.encode(lum[..., None]))
+
+
 def test_container_errors(native, golden):
     w = wts.random_init(0, True)
     codec = native_codec.Codec(w, True)
