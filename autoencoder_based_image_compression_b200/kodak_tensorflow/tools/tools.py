@@ -189,3 +189,26 @@ def subdivide_set(nb_examples, batch_size):
     if nb_examples % batch_size != 0:
         raise ValueError('`nb_examples` is not divisible by `batch_size`.')
     return nb_examples//batch_size
+
+
+def compute_bjontegaard(rates_0, psnrs_0, rates_1, psnrs_1):
+    """tools.py:157-263: average per cent saving in bitrate between two rate-distortion curves (the figure
+    reconstructing_eae_kodak.py reports next to its curves). Cubic fit of log-rate against PSNR for each curve,
+    both integrated over the PSNR range the curves share. Host arithmetic (float64), same checks as the reference."""
+    (rates_0, psnrs_0, rates_1, psnrs_1) = (numpy.asarray(a) for a in (rates_0, psnrs_0, rates_1, psnrs_1))
+    if rates_0.ndim != 1:
+        raise ValueError('`rates_0.ndim` is not equal to 1.')
+    if rates_1.ndim != 1:
+        raise ValueError('`rates_1.ndim` is not equal to 1.')
+    if psnrs_0.shape != rates_0.shape:
+        raise ValueError('`psnrs_0.shape` is not equal to `rates_0.shape`.')
+    if psnrs_1.shape != rates_1.shape:
+        raise ValueError('`psnrs_1.shape` is not equal to `rates_1.shape`.')
+    for (name, values) in (('rates_0', rates_0), ('rates_1', rates_1), ('psnrs_0', psnrs_0), ('psnrs_1', psnrs_1)):
+        numpy.testing.assert_array_less(0., values, err_msg='An element of `{}` is not strictly positive.'.format(name))
+    (low, high) = (max(psnrs_0.min().item(), psnrs_1.min().item()), min(psnrs_0.max().item(), psnrs_1.max().item()))
+    mean_log_rate = []
+    for (rates, psnrs) in ((rates_0, psnrs_0), (rates_1, psnrs_1)):
+        primitive = numpy.polyint(numpy.polyfit(psnrs, numpy.log(rates), 3))
+        mean_log_rate.append(numpy.polyval(primitive, high) - numpy.polyval(primitive, low))
+    return 100.*(numpy.exp((mean_log_rate[1] - mean_log_rate[0])/(high - low)).item() - 1.)

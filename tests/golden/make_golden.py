@@ -249,6 +249,23 @@ def make_glue(ref_stats, tls):
     save('glue.npz', **out)
 
 
+def make_bjontegaard(tls):
+    """tools.py:157-263 on the reference's own test curves (test_tools.py:120-131) and on two 9-point curves."""
+    out = {}
+    rates_0 = numpy.linspace(0.15, 2.05, num=191)
+    rates_1 = numpy.linspace(0.1, 1.7, num=321)
+    out['case0__in'] = numpy.array([0.])
+    out['case0__out'] = numpy.array(tls.compute_bjontegaard(rates_0, 40.*numpy.sqrt(rates_0), rates_1, 20.*numpy.sqrt(rates_1) + 10.))
+    rng = numpy.random.default_rng(11)
+    r0 = numpy.sort(0.1 + 1.9*rng.random(9))
+    r1 = numpy.sort(0.1 + 1.9*rng.random(9))
+    p0 = 28. + 6.*numpy.log2(1. + 4.*r0) + 0.05*rng.standard_normal(9)
+    p1 = 27. + 6.2*numpy.log2(1. + 4.*r1) + 0.05*rng.standard_normal(9)
+    out['case1__in'] = numpy.stack([r0, p0, r1, p1])
+    out['case1__out'] = numpy.array(tls.compute_bjontegaard(r0, p0, r1, p1))
+    save('bjontegaard.npz', **out)
+
+
 if __name__ == '__main__':
     coder.build(force=True)
     assert coder.has_ref(), 'reference tree not available'
@@ -258,3 +275,4 @@ if __name__ == '__main__':
     (ref_compression, ref_stats, tls) = import_reference_python()
     make_compression(ref_compression, tables)
     make_glue(ref_stats, tls)
+    make_bjontegaard(tls)
