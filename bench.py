@@ -429,6 +429,13 @@ def run_gpu_arm(args):
     #  1593 MB with 3xTF32 everywhere).
     traffic = {'mixed': 1573.3e6, 'fp32': None}.get(args.math, 1593.3e6)
     traffic = traffic/13.*(n/24.)*scale if traffic else None
+    # cuBLAS TF32 throughput measured on this pool's B200 (scripts/measure_tf32_peak.py), for information: the fraction is
+    # taken against the (higher) bf16 / 2 figure derived from MEASURED_PEAKS.json.
+    tf32_cublas = None
+    tf32_path = os.path.join(ROOT, 'profiles', 'r01_tf32_peak.json')
+    if os.path.isfile(tf32_path):
+        with open(tf32_path) as f:
+            tf32_cublas = json.load(f)
     line['roofline'] = {
         'bound': 'tensor', 'kernel': 'tap-list implicit GEMM (convs, transposed convs, GDN/IGDN), math=' + args.math,
         'achieved': achieved, 'peak': bf16_peak/2., 'unit': 'TFLOP/s',
@@ -440,6 +447,8 @@ def run_gpu_arm(args):
         'avg_launch_ms': gemm_ms/gemm_launches if gemm_launches else None,
         'share_of_step': gemm_ms/serial_ms if serial_ms else None,
         'executed_mma_tflops': executed, 'frac_executed': executed/(bf16_peak/2.) if bf16_peak else None,
+        'tf32_cublas_measured_tflops': {'burst': tf32_cublas['tf32_tflops'], 'sustained': tf32_cublas['tf32_tflops_sustained']}
+                                       if tf32_cublas else None,
         'note': 'achieved / frac count ALGORITHMIC flops (SURVEY 8d). tf32x3 issues 3 TF32 MMAs per product (frac <= 1/3 '
                 'by construction); mixed = 3 per product on the analysis side, which decides the indices, 1 on the synthesis '
                 'side, whose bar is the PSNR (frac <= 1/2); frac_executed is the tensor-pipe view of the same time; traffic = '
