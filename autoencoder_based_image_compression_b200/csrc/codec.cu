@@ -57,6 +57,7 @@ struct eae_codec {
     cudaEvent_t fork_event = nullptr, join_event = nullptr;
     int coder_priority = 0;
     int use_graphs = 1;            // env EAE_GRAPHS=0 disables the step graphs
+    int graphs_in_host_calls = 0;  // experiment: env EAE_GRAPHS_HOST=1
     bool host_call = false;        // set by the _host entry points: they launch directly (measured: with one host thread per
                                    // pipeline slot, 16 threads replaying graphs lose 4 % end to end, while the device-resident
                                    // entry points, driven by one thread, gain 6 %)
@@ -946,6 +947,7 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     if (const char* env = getenv("EAE_PHASE_MERGE")) c->phase_merge = atoi(env);
     if (const char* env = getenv("EAE_CODER_PRIORITY")) c->coder_priority = atoi(env);
     if (const char* env = getenv("EAE_GRAPHS")) c->use_graphs = atoi(env);
+    if (const char* env = getenv("EAE_GRAPHS_HOST")) c->graphs_in_host_calls = atoi(env);
     *out = c.release();
     return 0;
 }
@@ -1129,7 +1131,7 @@ extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm,
     if (c->rec_u8.bytes < dcap + 16) EAE_TRY(c->rec_u8.alloc(dcap + 16));
     EAE_CUDA_OK(cudaMemcpyAsync(c->img_u8.p, img, nin, cudaMemcpyHostToDevice, st));
     if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
-    c->host_call = true;
+    c->host_call = !c->graphs_in_host_calls;
     struct Reset { eae_codec* c; ~Reset() { c->host_call = false; } } reset{c};
     EAE_TRY(compress_dev_impl(c, prm, c->img_u8.as<uint8_t>(), n, h, w, c->rec_u8.as<uint8_t>(), dcap,
                               c->total_bytes.as<uint64_t>(), nullptr, st));
@@ -1182,7 +1184,7 @@ extern "C" int eae_decompress_host(eae_codec_t* c, const eae_coding_params_t* pr
     const size_t nout = (size_t)n * h * w;
     if (c->img_u8.bytes < nout) EAE_TRY(c->img_u8.alloc(nout));
     EAE_CUDA_OK(cudaMemcpyAsync(c->rec_u8.p, container, nbytes, cudaMemcpyHostToDevice, st));
-    c->host_call = true;
+    c->host_call = !c->graphs_in_host_calls;
     struct Reset { eae_codec* c; ~Reset() { c->host_call = false; } } reset{c};
     EAE_TRY(decompress_dev_impl(c, prm, c->rec_u8.as<uint8_t>(), n, h, w, c->img_u8.as<uint8_t>(), st));
     // error of the lowest-numbered failing stream -> flag[1] -> mailbox; the reconstruction rides the same stream
