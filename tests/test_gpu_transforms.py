@@ -177,3 +177,29 @@ def test_mixed_mode_keeps_the_index_bar_and_the_psnr_bar(native):
     assert worst < 0.01
     assert delta.max() <= 1 and (delta != 0).mean() < 0.05
     assert rel < 5e-3
+
+
+def test_random_shapes_against_the_oracle(native):
+    """Seeded sweep over frame sizes that are multiples of 16 but of no tile size (first / last pixel blocks of the fused
+    last layer, partial 16 x 16 tiles of the tap-list GEMM, one-row and one-column latents), both variants of the
+    architecture, in the bench's default arithmetic: latents within the 3xTF32 tolerance, float reconstructions within
+    the single-pass tolerance, pixels never more than one grey level off."""
+    rng = numpy.random.default_rng(12)
+    shapes = [(16, 16*int(rng.integers(1, 20))) for _ in range(2)] + [(16*int(rng.integers(1, 20)), 16) for _ in range(2)] + \
+             [(16*int(rng.integers(1, 21)), 16*int(rng.integers(1, 21))) for _ in range(8)]
+    for (k, (h, wd)) in enumerate(shapes):
+        learned = bool(k & 1)
+        n = 1 + (k % 3)
+        w = visible_weights(20 + k, learned)
+        codec = native_codec.Codec(w, learned, math='mixed')
+        lum = util.synthetic_luma(rng, n, h, wd, smooth=bool(k & 2))[..., None]
+        y = codec.encode(lum)
+        y32 = T.encoder(lum.astype(numpy.float32), w, learned)
+        assert y.shape == y32.shape == (n, h//16, wd//16, 128)
+        assert numpy.abs(y - y32).max() < 2e-4*max(1., numpy.abs(y32).max()), (h, wd, learned)
+        q = numpy.round(y32)
+        want_f = T.decoder(q, w, learned)
+        rec_f = codec.decode_float(q)
+        assert numpy.abs(rec_f - want_f).max() < 1e-3*max(1., numpy.abs(want_f).max()), (h, wd, learned)
+        diff = numpy.abs(codec.decode(q).astype(numpy.int32) - oracle_glue.cast_bt601(want_f).astype(numpy.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 2e-2, (h, wd, learned, diff.max(), (diff != 0).mean())
