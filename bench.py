@@ -454,6 +454,26 @@ def run_gpu_arm(args):
                 'side, whose bar is the PSNR (frac <= 1/2); frac_executed is the tensor-pipe view of the same time; traffic = '
                 'dram read + write bytes per launch from the ncu capture under profiles/',
     }
+    # ---- the HBM-bound kernels (north star: achieved GB/s of the quantize and coder kernels against the measured peak) ----
+    hbm_peak = 6552.
+    if os.path.isfile(peaks_path):
+        with open(peaks_path) as f:
+            hbm_peak = float(json.load(f).get('hbm_gbs', hbm_peak))
+    idx_bytes = n*(h//16)*(w//16)*128*2               # int16 indices of the batch
+    stream_bytes = line['rate_bpp']*n*h*w/8.           # coded bytes of the batch
+    algorithmic = {'quantize': 3*idx_bytes,            # fp32 latent read, int16 planar indices written
+                   'dequantize': 3*idx_bytes,
+                   'coder_encode': idx_bytes + stream_bytes,
+                   'coder_decode': idx_bytes + stream_bytes,
+                   'pack': 2*stream_bytes}
+    line['hbm_kernels'] = {
+        k: {'algorithmic_bytes_per_step': float(b), 'ms_per_step': profile[k][1]/args.steps,
+            'achieved_gbs': float(b)/(profile[k][1]/args.steps)/1e6 if profile[k][1] > 0 else None,
+            'frac_of_hbm_peak': float(b)/(profile[k][1]/args.steps)/1e6/hbm_peak if profile[k][1] > 0 else None}
+        for (k, b) in algorithmic.items()}
+    line['hbm_kernels']['note'] = ('serial pass, CUDA events per kernel class; peak {:.0f} GB/s (MEASURED_PEAKS.json). The coder '
+                                   'kernels are latency-bound (one thread per coded stream, a dependent chain per bin), not '
+                                   'bandwidth-bound: their fraction is reported, not optimised for').format(hbm_peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = run_cpu_arm(args, steps=1, warmup=1, sample_per_core=16)
     if world > 1:
