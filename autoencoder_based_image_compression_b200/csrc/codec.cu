@@ -58,9 +58,9 @@ struct eae_codec {
     int coder_priority = 0;
     int use_graphs = 1;            // env EAE_GRAPHS=0 disables the step graphs
     int graphs_in_host_calls = 0;  // experiment: env EAE_GRAPHS_HOST=1
-    bool host_call = false;        // set by the _host entry points: they launch directly (measured: with one host thread per
-                                   // pipeline slot, 16 threads replaying graphs lose 4 % end to end, while the device-resident
-                                   // entry points, driven by one thread, gain 6 %)
+    bool host_call = false;        // set by the _host entry points: they launch directly (with one host thread per pipeline
+                                   // slot, replaying graphs changes the end-to-end rate by less than its run-to-run spread,
+                                   // while the device-resident entry points, driven by one thread, gain 6 %)
     uint64_t generation = 0;       // bumped whenever a device buffer of the codec is (re)allocated
     uint64_t graph_clock = 0;
     std::vector<StepGraph> graphs;

@@ -53,7 +53,7 @@ def parse_args():
                          'per GPU would otherwise spin on more threads than the box has cores); 0: driver default')
     ap.add_argument('--coder-lanes', type=int, default=1,
                     help='GPU threads per coded stream (0 = one warp per stream: lowest latency)')
-    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '16')),
+    ap.add_argument('--depth', type=int, default=int(os.environ.get('EAE_PIPELINE_DEPTH', '12')),
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')
     return ap.parse_args()
 
