@@ -743,6 +743,7 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
     if (cap < kHeaderBytes + 8ull * n_streams) { set_error("container capacity too small"); return EAE_ERR_ARGUMENT; }
     c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
+    c->last_idx_elems = (uint64_t)n_streams * hw3;      // (host state: outside the body, which may be replayed as a graph)
     // parts: as encode_chunk's (1 = layer 1 has already been launched)
     auto body = [&](cudaStream_t st, int parts) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
@@ -755,7 +756,6 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
                                           c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3, nullptr,
                                           nc, hw3, c->flag.as<uint32_t>(), st));
     }
-    c->last_idx_elems = (uint64_t)n_streams * hw3;
     cudaStream_t cs = st;
     EAE_TRY(fork_coder_stream(c, st, &cs));
     {
@@ -805,6 +805,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     EAE_TRY(ensure_workspace(c, n < chunk ? n : chunk, h, w));
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
     c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
+    c->last_idx_elems = (uint64_t)n_streams * hw3;
     auto body = [&](cudaStream_t st) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
     cudaStream_t cs = st;
@@ -825,7 +826,6 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
                                       c->row_flags.as<uint8_t>()));
     }
     EAE_TRY(join_coder_stream(c, st, cs));
-    c->last_idx_elems = (uint64_t)n_streams * hw3;
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
         const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
         // the dequantized latent lives in bufA's tail-free region: use buf3 when IGDN4 is absent,

@@ -182,6 +182,9 @@ def test_repeated_steps_replay_a_graph_with_identical_results(native, golden):
         assert size == want.size and numpy.array_equal(d_cont.cpu().numpy()[:size], want), (k, i, j)
         assert numpy.array_equal(d_rec.cpu().numpy(), plain.decompress(want, prms[j])), (k, i, j)
     assert len(set(launches[1:5])) == 1, launches      # direct, captured and replayed steps count the same launches
+    # host-side state after a replayed step: the indices of the last step can be fetched
+    plain.compress(images[0], prms[0])
+    assert numpy.array_equal(codec.last_indices(n, h, wd), plain.last_indices(n, h, wd))
 
 
 def test_batches_larger_than_the_workspace_chunk(native, golden, monkeypatch):
