@@ -2849,6 +2849,11 @@ int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8
 {
     if (!n) return 0;
     if (H % 4 != 0 || W % 4 != 0 || !w.hi || (exact3x && !w.lo)) { set_error("tconv9s4: bad arguments"); return EAE_ERR_ARGUMENT; }
+    // the gather stores pixel pairs (uchar2 / float2)
+    if ((reinterpret_cast<uintptr_t>(out_u8) & 1u) || (reinterpret_cast<uintptr_t>(out_f32) & 7u)) {
+        set_error("tconv9s4: the reconstruction buffer must be 2-byte (uint8) / 8-byte (float) aligned");
+        return EAE_ERR_ARGUMENT;
+    }
     if (!g_error_flag) {
         EAE_CUDA_OK(cudaMalloc(&g_error_flag, 4));
         EAE_CUDA_OK(cudaMemset(g_error_flag, 0, 4));
