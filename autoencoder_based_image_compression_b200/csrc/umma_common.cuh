@@ -1,0 +1,154 @@
+// Constants, parameter blocks and PTX wrappers shared by every generation of the tcgen05 tap-list GEMM (conv_umma.cu).
+// Private to conv_umma.cu (one translation unit): everything here sits in its anonymous namespace.
+#pragma once
+
+#include <cuda.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "conv_plan.cuh"
+
+namespace eae {
+namespace {
+
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int kTileBytes = kTileM * 128;    // 16 KB: 128 rows x 128 bytes
+constexpr int kUmmaThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue / A split
+constexpr uint32_t kTmemCols = 128;
+constexpr long long kTimeoutCycles = 400ll * 1000 * 1000;   // ~0.2 s
+
+template <bool kExact> struct Cfg {
+    static constexpr int kStageBytes = kExact ? 4 * kTileBytes : 2 * kTileBytes;   // A [A_lo] B [B_lo]
+    static constexpr int kStages = kExact ? 3 : 6;
+    static constexpr int kOffAlo = kTileBytes;
+    static constexpr int kOffBhi = kExact ? 2 * kTileBytes : kTileBytes;
+    static constexpr int kOffBlo = 3 * kTileBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+struct UmmaTap { int plane, fy, fx, w_tap; };
+
+struct UmmaParams {
+    int n_taps, kchunks;
+    int tile_w, tile_h, tiles_x, tiles_y;
+    int Hg, Wg;
+    float* out;
+    const float* bias;
+    const float* xin;        // GDN / IGDN: the un-squared input, same flat [M,128] indexing as `out`
+    int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int mode;                // EpilogueMode
+    uint32_t* error_flag;
+    UmmaTap taps[kMaxTaps];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: false (and the error flag set) if the phase does not complete in time.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* error_flag, uint32_t who)
+{
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > kTimeoutCycles) {
+            atomicOr(error_flag, 1u << who);
+            return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor bit layout): start >> 4 in
+// [0,14), LBO in [16,30) (unused here: one swizzle atom along K), SBO = 1024 B (8 rows x 128 B) in
+// [32,46), version 1 in [46,48), layout SWIZZLE_128B (2) in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32, D fp32, A/B K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor bit layout).
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+// One lane of a converged warp (elect.sync): the MMA warp runs its loop with all lanes and issues from the elected
+// one, so that every tcgen05 operand is a warp-uniform value (see the note on kTmemBase0).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace
+}  // namespace eae

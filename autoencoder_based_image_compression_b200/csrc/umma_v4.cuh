@@ -1,0 +1,296 @@
+// Version 4 (default for the multi-tap layers): union activation boxes, one commit per iteration, merged output phases.
+// Private to conv_umma.cu (one translation unit): everything here sits in its anonymous namespace.
+#pragma once
+
+#include "umma_v3.cuh"
+
+namespace eae {
+namespace {
+
+// =================================================================================================
+// Version 4 (default for the multi-tap layers): version 3 with every activation box fetched ONCE.
+//
+// Measured on version 3 (profiles/r01_ncu_full_gemm_umma3_layers.md): a ring iteration of a k5 layer moves
+// 64 KB from L2 into shared memory (two 16 KB activation boxes + 32 KB of split weights) for 24 MMAs, i.e.
+// the kernel asks for ~42 B/clk/SM against an L2 throughput cap of ~43 B/clk/SM (6.3 KB/clk over 148 SMs),
+// and the conversion warps spend 38 % of their samples waiting for TMA data: iterations take 1.95 k cycles
+// instead of the 1.54 k the MMAs need. But the boxes of the taps of one input plane are the same pixels shifted
+// by one position: the 9 taps of the (odd, odd) parity plane of a k5 s2 convolution overlap in 15/16 of their
+// rows. Here the loop runs channel chunk -> tap group -> tap, the UNION box of a group (18 x 18 positions x 32
+// channels, 41 KB) is loaded once into one of two buffers, and the conversion warps read each tap's rows from
+// it at a shifted offset; only the weights stream per tap (32 KB stages, 4 deep). Activation traffic drops from
+// 3.2 MB to 0.65 MB per 256-position tile of a 25-tap layer (total L2 -> SM traffic -40 %).
+//
+//  smem: union buffers 2 x 41 KB | weight stages 4 x { B_hi 16K | B_lo 16K } | barriers. The fused GDN phase and
+//        the epilogue alias the first 192 KB as in version 3 (3 stages x 64 KB), after the main loop has drained.
+constexpr int kUnionW = 18, kUnionH = 18;
+constexpr int kUnionTx = kUnionW * kUnionH * 128;          // bytes one union load delivers
+constexpr int kUnionBytes = 41 * 1024;
+constexpr int kBStages4 = 4, kBStageBytes4 = 2 * kTileBytes;
+constexpr int kOffB4 = 2 * kUnionBytes;
+constexpr int kOffBars4 = kOffB4 + kBStages4 * kBStageBytes4;
+constexpr int kSmemBytes4 = kOffBars4 + 512 + 1024;
+constexpr int kGdnStageBytes4 = 4 * kTileBytes;
+static_assert(3 * kGdnStageBytes4 <= kOffBars4, "GDN / epilogue stages must fit below the barriers");
+constexpr int kMaxGroups4 = 4;
+
+struct UmmaTap4 { int w_tap, off, grp, last; };            // off: row offset of this tap's box inside its group's union
+struct UmmaGroup4 { int plane, fy, fx, pad; };             // union origin relative to the tile origin
+struct UmmaParams4 {
+    int n_taps, kchunks, n_groups;
+    int tiles_x, tiles_y, Hg, Wg;
+    float* out;
+    const float* bias;
+    const float* beta;
+    int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int fuse, exact_main, exact_gdn;
+    long long* times;
+    uint32_t* error_flag;
+    UmmaTap4 taps[kMaxTaps];
+    UmmaGroup4 groups[kMaxGroups4];
+};
+
+// Up to four launches that read the same input through the same weight array (the four output phases of a transposed
+// convolution) run as ONE grid: CTA b works on tile b / n_phases of phase b % n_phases. The phases of a tile are neighbours
+// in the grid, so the input box they share is fetched from HBM once; and six dependent launches per step disappear
+// (beside other streams' kernels a dependent launch waits ~10 us).
+struct UmmaParams4x {
+    int n_phases, pad;
+    UmmaParams4 ph[4];
+};
+
+__global__ void __maxnreg__(kMaxRegs34)
+gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
+                  const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4x pp)
+{
+    const UmmaParams4& p = pp.ph[blockIdx.x % (unsigned)pp.n_phases];
+    const int tile_linear = (int)(blockIdx.x / (unsigned)pp.n_phases);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars4);
+    uint64_t* b_full = bars;               // [4] weight stage landed
+    uint64_t* done = bars + 4;             // [4] the MMAs of iteration it (it & 3) completed: ONE commit per iteration
+                                           //     releases the weight stage (it + 4), the TMEM A slot (it + 2) and, after the
+                                           //     last tap of a group, its union buffer (a tcgen05.commit costs ~100 cycles of
+                                           //     tensor-pipe time, three per iteration made the loop 15 % slower)
+    uint64_t* u_full = bars + 8;           // [2] union box landed
+    uint64_t* split = bars + 12;           // [4] TMEM A slot of iteration it (it & 3) written (one arrival per conversion warp)
+    uint64_t* acc_full = bars + 16;
+    uint64_t* nrm_full = bars + 17;
+    const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
+                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 12 : nullptr;      // [8] start ns, [9] end ns, [10] SM id
+    if (stamp && threadIdx.x == 64) {
+        stamp[0] = clock64();
+        uint32_t smid;
+        long long t;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamp[8] = t; stamp[10] = smid;
+    }
+    // tile = 16 x 16 positions: half h covers rows [a0 + 8 h, + 8)
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int img = tile_linear / tiles_per_img;
+    const int trem = tile_linear - img * tiles_per_img;
+    const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
+        for (int s = 0; s < 2; s++) mbar_init(&u_full[s], 1);
+        for (int s = 0; s < 4; s++) mbar_init(&split[s], 4);      // one arrival per conversion warp
+        gdn_tail_ts_init(tail);
+        mbar_init(acc_full, 1);
+        mbar_init(nrm_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // This CTA owns the whole TMEM of its SM (512 columns, 1 CTA per SM), so the allocation starts at column 0. The
+    // MMA-issuing thread uses that CONSTANT: with the base read from shared memory every tcgen05.mma operand went
+    // through an ELECT / R2UR / BRA.U.ANY waterfall (~80 cycles of issue per MMA, more than the 64 it executes).
+    if (tmem_base != kTmemBase0 && threadIdx.x == 0) atomicOr(p.error_flag, 1u << 8);
+    if (stamp && threadIdx.x == 64) stamp[1] = clock64();
+
+    const int n_main = p.n_taps * p.kchunks;      // iteration it = kc * n_taps + t
+    const int n_gdn = p.fuse ? 8 : 0;             // (half, gamma chunk) pairs
+    const int n_unions = p.kchunks * p.n_groups;  // union g = kc * n_groups + group
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            bool ok = true;
+            int issued = 0;                       // unions requested so far
+            for (int it = 0; it < n_main && ok; it++) {
+                const int kc = it / p.n_taps, t = it - kc * p.n_taps;
+                const UmmaTap4 tap = p.taps[t];
+                const int g = kc * p.n_groups + tap.grp;
+                // the union this tap reads, and (without waiting) the one after it as soon as its buffer is free
+                while (ok && issued < n_unions && issued <= g + 1) {
+                    const int buf = issued & 1;
+                    if (issued >= 2) {
+                        // the buffer held union issued - 2: free once the MMAs of that group's last tap are done
+                        const int pk = (issued - 2) / p.n_groups, pg = (issued - 2) - pk * p.n_groups;
+                        const int last_it = pk * p.n_taps + p.groups[pg].pad;      // pad = index of the group's last tap
+                        const uint32_t par = (uint32_t)(last_it >> 2) & 1u;
+                        if (issued <= g) ok = mbar_wait(&done[last_it & 3], par, p.error_flag, 0);
+                        else if (!mbar_try(&done[last_it & 3], par)) break;
+                        if (!ok) break;
+                    }
+                    const UmmaGroup4 grp = p.groups[issued % p.n_groups];
+                    mbar_expect_tx(&u_full[buf], kUnionTx);
+                    tma_load_5d(smem + buf * kUnionBytes, &map_u, &u_full[buf], (issued / p.n_groups) * kChunkK, b0 + grp.fx,
+                                a0 + grp.fy, grp.plane, img);
+                    issued++;
+                }
+                if (!ok) break;
+                const int s = it & 3;
+                if (!mbar_wait(&done[s], ((uint32_t)(it >> 2) & 1u) ^ 1u, p.error_flag, 0)) { ok = false; break; }
+                uint8_t* st = smem + kOffB4 + s * kBStageBytes4;
+                mbar_expect_tx(&b_full[s], (p.exact_main ? 2 : 1) * kTileBytes);
+                tma_load_3d(st, &map_b_hi, &b_full[s], kc * kChunkK, 0, tap.w_tap);
+                if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &b_full[s], kc * kChunkK, 0, tap.w_tap);
+            }
+            if (ok && n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+        {
+            bool ok = true;
+            for (int it = 0; it < n_main && ok; it++) {
+                const int slot_i = it & 1, s = it & 3;
+                ok = mbar_wait(&split[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
+                if (ok) ok = mbar_wait(&b_full[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
+                ok = __all_sync(0xFFFFFFFFu, ok);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smem + kOffB4 + s * kBStageBytes4);
+                    // single pass: the lo columns of a set's slot are a second hi slot (iterations it, it + 2 of the set)
+                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i +
+                                          (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t d = kTmemBase0 + (h ? kCol3Acc1 : kCol3Acc0);
+                        const uint32_t a_hi = slot + 64u * (uint32_t)h, a_lo = a_hi + 32u;
+                        #pragma unroll
+                        for (int k = 0; k < kChunkK / 8; k++) {
+                            const uint64_t b_hi = make_desc(st + k * 32);
+                            umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
+                            if (p.exact_main) {
+                                umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
+                                umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
+                            }
+                        }
+                    }
+                    umma_commit(&done[s]);
+                    if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
+                }
+                __syncwarp();
+            }
+            if (ok && n_gdn) gdn_tail_ts_mma(tail, p.error_flag);
+        }
+    } else {
+        // ===== warps 2..9: two conversion / epilogue sets; set k owns TMEM A slot k and the iterations of parity k
+        const int quarter = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t slot_set = lane_base + kCol3Slots + 128u * (uint32_t)set;
+        const int reuse = p.exact_main ? 2 : 4;      // the slot written now was read by the MMAs of iteration it - reuse
+        const int row_in_union = (row >> 4) * kUnionW + (row & 15);     // half 1 adds 8 union rows
+        bool ok = true;
+        uint32_t r[32], hi[32];
+        for (int it = set; it < n_main && ok; it += 2) {
+            const int kc = it / p.n_taps, t = it - kc * p.n_taps;
+            const UmmaTap4 tap = p.taps[t];
+            const int g = kc * p.n_groups + tap.grp;
+            ok = mbar_wait(&u_full[g & 1], (uint32_t)(g >> 1) & 1u, p.error_flag, 2);
+            if (!ok) break;
+            if (stamp && it == 0 && threadIdx.x == 64) stamp[2] = clock64();
+            // Read both halves' rows first: the shared-memory reads do not depend on the TMEM slot, so they overlap the
+            // wait for the MMAs of iteration it - 2 (the completion -> conversion -> issue chain paces the loop).
+            const uint8_t* ubuf = smem + (g & 1) * kUnionBytes;
+            #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int ur = row_in_union + h * 8 * kUnionW + tap.off;
+                const uint8_t* rowp = ubuf + ur * 128;
+                uint32_t* dst = h ? hi : r;
+                #pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (ur & 7)) << 4));
+                    dst[4 * c + 0] = __float_as_uint(v.x); dst[4 * c + 1] = __float_as_uint(v.y);
+                    dst[4 * c + 2] = __float_as_uint(v.z); dst[4 * c + 3] = __float_as_uint(v.w);
+                }
+            }
+            const uint32_t slot = slot_set + (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
+            if (it >= reuse) {
+                ok = mbar_wait(&done[(it - reuse) & 3], (uint32_t)((it - reuse) >> 2) & 1u, p.error_flag, 5);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x). Single pass: round to nearest
+            // instead (add half a TF32 ulp to the magnitude before the truncation) - truncation shrinks every product by
+            // 2^-12 on average, a bias that does not average out over the ~1 200 terms of a sum.
+            if (!p.exact_main) {
+                #pragma unroll
+                for (int i = 0; i < 32; i++) { r[i] += 0x1000u; hi[i] += 0x1000u; }
+            }
+            tmem_st32(slot, r);
+            tmem_st32(slot + 64u, hi);
+            if (p.exact_main) {
+                #pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
+                    hi[i] = __float_as_uint(__uint_as_float(hi[i]) - __uint_as_float(hi[i] & 0xFFFFE000u));
+                }
+                tmem_st32(slot + 32u, r);
+                tmem_st32(slot + 96u, hi);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[it & 3]);   // 4 arrivals instead of 128: the arrive chain is on the critical path
+        }
+        const int wq = warp - 2;
+        const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
+        uint8_t* stage0 = smem;                          // un-fused epilogue: both halves staged side by side
+        uint8_t* stage1 = smem + kGdnStageBytes4;
+        if (ok && n_gdn) {
+            ok = gdn_tail_ts_run(tail, set, row, lane, wq, lane_base, p.fuse, p.bias, p.beta, geom, p.error_flag, stamp);
+        } else {
+            if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (stamp && threadIdx.x == 64) stamp[5] = clock64();
+            stage_tile(smem, kGdnStageBytes4, lane_base, set, row, false, 0, p.bias, p.beta);
+            named_bar_sync(1, 256);     // both sets finished staging
+            if (stamp && threadIdx.x == 64) stamp[6] = clock64();
+            store_half4(geom, stage0, 0, wq, lane, ok);
+            store_half4(geom, stage1, 1, wq, lane, ok);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (stamp && threadIdx.x == 64) {
+        stamp[7] = clock64();
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamp[9] = t;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+    }
+}
+
+}  // namespace
+}  // namespace eae
