@@ -68,46 +68,59 @@ def gdn(x_nhwc, gamma, beta, inverse=False):
     return out.reshape(shape)
 
 
-def encoder(visible_units_nhwc, weights, are_bin_widths_learned, dtype=torch.float32):
-    """components.encoder (components.py:86-142). Input float array [B,h,w,1], raw 0..255."""
+# The layer tables below ARE what encoder() / decoder() execute. tests/test_graph_structure.py compares them, entry by
+# entry, with the op chain, the strides / padding / data format and the variable names and shapes of the reference's own
+# serialised graphs (kodak_tensorflow/eae/results/*/model_*.ckpt.meta, parsed into tests/golden/graph_structure.json):
+# the STRUCTURE of this restatement is pinned to a reference-held artefact, its arithmetic is restated.
+# `optional`: the non-linearity exists only when the bin widths are NOT learned (components.py:56-58, 138-141).
+ENCODER_LAYERS = (
+    {'conv': 'encoder/weights_1', 'stride': STRIDES[0], 'bias': 'encoder/biases_1',
+     'gdn': ('encoder/gamma_1', 'encoder/beta_1'), 'optional': False},
+    {'conv': 'encoder/weights_2', 'stride': STRIDES[1], 'bias': 'encoder/biases_2',
+     'gdn': ('encoder/gamma_2', 'encoder/beta_2'), 'optional': False},
+    {'conv': 'encoder/weights_3', 'stride': STRIDES[2], 'bias': 'encoder/biases_3',
+     'gdn': ('encoder/gamma_3', 'encoder/beta_3'), 'optional': True},
+)
+# The inverse GDN comes BEFORE the transposed convolution of the same index (components.py:56-84).
+DECODER_LAYERS = (
+    {'igdn': ('decoder/gamma_4', 'decoder/beta_4'), 'optional': True,
+     'tconv': 'decoder/weights_4', 'stride': STRIDES[2], 'bias': 'decoder/biases_4'},
+    {'igdn': ('decoder/gamma_5', 'decoder/beta_5'), 'optional': False,
+     'tconv': 'decoder/weights_5', 'stride': STRIDES[1], 'bias': 'decoder/biases_5'},
+    {'igdn': ('decoder/gamma_6', 'decoder/beta_6'), 'optional': False,
+     'tconv': 'decoder/weights_6', 'stride': STRIDES[0], 'bias': None},      # no bias: components.py:79-84
+)
+
+
+def encoder_stages(visible_units_nhwc, weights, are_bin_widths_learned, dtype=torch.float32):
+    """Per-layer outputs [gdn_1, gdn_2, y] of components.encoder (components.py:86-142). Input [B,h,w,1], raw 0..255."""
     w = {k: _t(v, dtype) for (k, v) in weights.items() if k.startswith('encoder/')}
     x = _t(visible_units_nhwc, dtype)
-    x = gdn(conv2d_same(x, w['encoder/weights_1'], STRIDES[0]) + w['encoder/biases_1'],
-            w['encoder/gamma_1'], w['encoder/beta_1'])
-    x = gdn(conv2d_same(x, w['encoder/weights_2'], STRIDES[1]) + w['encoder/biases_2'],
-            w['encoder/gamma_2'], w['encoder/beta_2'])
-    x = conv2d_same(x, w['encoder/weights_3'], STRIDES[2]) + w['encoder/biases_3']
-    if not are_bin_widths_learned:
-        x = gdn(x, w['encoder/gamma_3'], w['encoder/beta_3'])
-    return x.numpy()
+    stages = []
+    for layer in ENCODER_LAYERS:
+        x = conv2d_same(x, w[layer['conv']], layer['stride']) + w[layer['bias']]
+        if not (layer['optional'] and are_bin_widths_learned):
+            x = gdn(x, w[layer['gdn'][0]], w[layer['gdn'][1]])
+        stages.append(x.numpy())
+    return stages
+
+
+def encoder(visible_units_nhwc, weights, are_bin_widths_learned, dtype=torch.float32):
+    """components.encoder (components.py:86-142). Input float array [B,h,w,1], raw 0..255."""
+    return encoder_stages(visible_units_nhwc, weights, are_bin_widths_learned, dtype)[-1]
 
 
 def decoder(quantized_y_nhwc, weights, are_bin_widths_learned, dtype=torch.float32):
     """components.decoder (components.py:11-84). The last layer has no bias (:79-84)."""
     w = {k: _t(v, dtype) for (k, v) in weights.items() if k.startswith('decoder/')}
     x = _t(quantized_y_nhwc, dtype)
-    if not are_bin_widths_learned:
-        x = gdn(x, w['decoder/gamma_4'], w['decoder/beta_4'], inverse=True)
-    x = gdn(conv2d_transpose_same(x, w['decoder/weights_4'], STRIDES[2]) + w['decoder/biases_4'],
-            w['decoder/gamma_5'], w['decoder/beta_5'], inverse=True)
-    x = gdn(conv2d_transpose_same(x, w['decoder/weights_5'], STRIDES[1]) + w['decoder/biases_5'],
-            w['decoder/gamma_6'], w['decoder/beta_6'], inverse=True)
-    x = conv2d_transpose_same(x, w['decoder/weights_6'], STRIDES[0])
+    for layer in DECODER_LAYERS:
+        if not (layer['optional'] and are_bin_widths_learned):
+            x = gdn(x, w[layer['igdn'][0]], w[layer['igdn'][1]], inverse=True)
+        x = conv2d_transpose_same(x, w[layer['tconv']], layer['stride'])
+        if layer['bias'] is not None:
+            x = x + w[layer['bias']]
     return x.numpy()
-
-
-def encoder_stages(visible_units_nhwc, weights, are_bin_widths_learned, dtype=torch.float32):
-    """Per-layer outputs [gdn_1, gdn_2, y] for layer-by-layer parity tests."""
-    w = {k: _t(v, dtype) for (k, v) in weights.items() if k.startswith('encoder/')}
-    x = _t(visible_units_nhwc, dtype)
-    a1 = gdn(conv2d_same(x, w['encoder/weights_1'], STRIDES[0]) + w['encoder/biases_1'],
-             w['encoder/gamma_1'], w['encoder/beta_1'])
-    a2 = gdn(conv2d_same(a1, w['encoder/weights_2'], STRIDES[1]) + w['encoder/biases_2'],
-             w['encoder/gamma_2'], w['encoder/beta_2'])
-    y = conv2d_same(a2, w['encoder/weights_3'], STRIDES[2]) + w['encoder/biases_3']
-    if not are_bin_widths_learned:
-        y = gdn(y, w['encoder/gamma_3'], w['encoder/beta_3'])
-    return [a1.numpy(), a2.numpy(), y.numpy()]
 
 
 # ---------------------------------------------------------------------------------------------
