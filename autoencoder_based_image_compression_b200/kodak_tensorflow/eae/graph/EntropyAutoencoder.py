@@ -28,10 +28,12 @@ class _Model(object):
                 h_in, w_in, self.h_in, self.w_in))
 
     def initialization(self, sess, path_to_restore, seed=0):
-        """EntropyAutoencoder.py:440-463. ``path_to_restore`` is an ``.npz`` written by
-        ``weights.save`` (keys = TF variable names); an empty string draws a random initialisation."""
+        """EntropyAutoencoder.py:440-463. ``path_to_restore`` names an ``.npz`` written by ``weights.save`` (keys = TF
+        variable names): the file itself, or the reference's ``.../model_k.ckpt`` prefix next to which
+        ``model_k.ckpt.npz`` / ``model_k.npz`` lies (so the reference's drivers run with their own paths).
+        An empty string draws a random initialisation."""
         if path_to_restore:
-            self.weights = wts.load(path_to_restore)
+            self.weights = wts.load(wts.resolve_path(path_to_restore))
         else:
             self.weights = wts.random_init(seed, self.are_bin_widths_learned, getattr(self, 'bin_width_init', 1.))
         self._codec = None

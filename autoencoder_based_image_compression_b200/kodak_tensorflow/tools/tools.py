@@ -184,6 +184,46 @@ def rate_3d(quantized_latent_float32, bin_widths, h_in, w_in):
     return cumulated_rate/(h_in*w_in)
 
 
+def save_image(path, array_uint8):
+    """tools.py:1082-1106."""
+    import PIL.Image
+    if array_uint8.dtype != numpy.uint8:
+        raise TypeError('`array_uint8.dtype` is not equal to `numpy.uint8`.')
+    PIL.Image.fromarray(array_uint8).save(path)
+
+
+def crop_repeat_2d(image_uint8, row_top_left, column_top_left):
+    """tools.py:441-484: an 80 x 80 crop, every pixel repeated twice in both directions."""
+    if image_uint8.dtype != numpy.uint8:
+        raise TypeError('`image_uint8.dtype` is not equal to `numpy.uint8`.')
+    (height_image, width_image) = image_uint8.shape
+    if row_top_left + 80 >= height_image:
+        raise ValueError('`image_uint8.shape[0]` is not strictly larger than `row_top_left + 80`.')
+    if column_top_left + 80 >= width_image:
+        raise ValueError('`image_uint8.shape[1]` is not strictly larger than `column_top_left + 80`.')
+    return numpy.kron(image_uint8[row_top_left:row_top_left + 80, column_top_left:column_top_left + 80],
+                      numpy.ones((2, 2), dtype=numpy.uint8))
+
+
+def visualize_crops(image_uint8, positions_top_left, paths):
+    """tools.py:1172-1218: one saved crop per column of `positions_top_left`."""
+    if positions_top_left.ndim != 2 or positions_top_left.shape[0] != 2:
+        raise ValueError('`positions_top_left.shape[0]` is not equal to 2.')
+    if len(paths) != positions_top_left.shape[1]:
+        raise ValueError('`len(paths)` is not equal to `positions_top_left.shape[1]`.')
+    for (i, path) in enumerate(paths):
+        save_image(path, crop_repeat_2d(image_uint8, positions_top_left[0, i].item(), positions_top_left[1, i].item()))
+
+
+def visualize_rotated_luminance(luminance_before_rotation_uint8, is_rotated, positions_top_left, paths):
+    """tools.py:1292-1330: the (possibly rotated) luminance image and its crops as PNG files. Host-side diagnostics the
+    reference's evaluation loops call once per image (reconstructing_eae_kodak.py:229-232, 552-555); not on the GPU path."""
+    image_uint8 = numpy.rot90(luminance_before_rotation_uint8, k=3).copy() if is_rotated \
+        else luminance_before_rotation_uint8.copy()
+    visualize_crops(image_uint8, positions_top_left, paths[1:])
+    save_image(paths[0], image_uint8)
+
+
 def subdivide_set(nb_examples, batch_size):
     """tools.py:1108-1132."""
     if nb_examples % batch_size != 0:

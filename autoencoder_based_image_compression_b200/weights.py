@@ -80,6 +80,19 @@ def save(path, weights):
     numpy.savez(path, **{k.replace('/', '.'): v for (k, v) in weights.items()})
 
 
+def resolve_path(path_to_restore):
+    """The ``.npz`` behind a restore path: the path itself, ``<path>.npz`` or, for the reference's ``model_k.ckpt``
+    checkpoint prefixes (reconstructing_eae_kodak.py:118), ``model_k.npz``."""
+    import os
+    candidates = [path_to_restore, path_to_restore + '.npz']
+    if path_to_restore.endswith('.ckpt'):
+        candidates.append(path_to_restore[:-len('.ckpt')] + '.npz')
+    for candidate in candidates:
+        if os.path.isfile(candidate):
+            return candidate
+    raise IOError('no weight file at {} (tried {})'.format(path_to_restore, ', '.join(candidates[1:])))
+
+
 def load(path):
     with numpy.load(path) as data:
         return {k.replace('.', '/'): data[k] for k in data.files}

@@ -167,7 +167,8 @@ def test_drop_in_module_names_resolve(tmp_path):
     code = ("import sys; sys.path.insert(0, {root!r}); "
             "sys.path.insert(0, {root!r} + '/autoencoder_based_image_compression_b200/kodak_tensorflow'); "
             "import eae.batching, lossless.compression, lossless.interface_cython, lossless.stats, tools.tools as tls; "
-            "import reconstructing_eae_kodak; assert callable(reconstructing_eae_kodak.fix_gamma); "
+            "import tensorflow as tf; assert callable(tf.reset_default_graph) and hasattr(tf.Session(), '__enter__'); "
+            "assert callable(tls.visualize_rotated_luminance); "
             "assert tls.float_to_str(0.5) == '0dot5' and tls.float_to_str(10000.) == '10000' and tls.float_to_str(-1.5) == 'minus1dot5'; "
             "from eae.graph.EntropyAutoencoder import EntropyAutoencoder; "
             "from eae.graph.IsolatedDecoder import IsolatedDecoder; "
@@ -257,3 +258,30 @@ def test_last_layer_tile_gather_covers_every_pixel_once_in_col2im_order():
                     written[oy, ox:ox + 2] += 1
         assert (written == 1).all()
         assert numpy.array_equal(got, want)
+
+
+def test_the_reference_driver_imports_unmodified_on_the_mirror_packages():
+    """CPU half of tests/test_gpu_reference_driver.py: the reference's own script, read from where it lies, imports with
+    the mirror directory on sys.path (its tensorflow / eae / lossless / tools imports resolve to this package)."""
+    from tests import refdrivers
+    rek = refdrivers.load('reconstructing_eae_kodak.py')
+    if rek is None:
+        pytest.skip('reference driver not available')
+    assert callable(rek.fix_gamma) and callable(rek.vary_gamma_fix_bin_widths)
+    assert rek.tf.__file__.startswith(refdrivers.MIRROR)
+    assert rek.eae.batching.__file__.startswith(refdrivers.MIRROR)
+    assert rek.lossless.compression.__file__.startswith(refdrivers.MIRROR)
+    assert rek.tls.__file__.startswith(refdrivers.MIRROR)
+    stats_driver = refdrivers.load('collecting_stats_eae_extra.py')
+    assert stats_driver is not None and stats_driver.lossless.stats.__file__.startswith(refdrivers.MIRROR)
+
+
+def test_restore_path_resolution(tmp_path):
+    from autoencoder_based_image_compression_b200 import weights as wts
+    w = wts.random_init(0, True)
+    wts.save(str(tmp_path / 'model_10.npz'), w)
+    assert wts.resolve_path(str(tmp_path / 'model_10.ckpt')) == str(tmp_path / 'model_10.npz')
+    assert wts.resolve_path(str(tmp_path / 'model_10')) == str(tmp_path / 'model_10.npz')
+    assert sorted(wts.load(wts.resolve_path(str(tmp_path / 'model_10.ckpt')))) == sorted(w)
+    with pytest.raises(IOError):
+        wts.resolve_path(str(tmp_path / 'model_11.ckpt'))
