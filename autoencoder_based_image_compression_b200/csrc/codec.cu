@@ -252,7 +252,7 @@ int run_gemm(eae_codec* c, const GemmPlan& plan, int kind, const UmmaWeights& uw
 // Can the GDN / IGDN that follows a contraction of this kind run inside its epilogue?
 bool can_fuse(const eae_codec* c, int kind)
 {
-    return c->math != EAE_MATH_FP32_SIMT && umma_version() >= 2 && ((c->umma_mask >> kind) & 1) &&
+    return c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kind) & 1) &&
            ((c->umma_mask >> kLayerGdn) & 1) && !c->no_fuse;
 }
 
@@ -369,7 +369,7 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     // stride-2 layer that follows. On the tensor path (kernel version 3) the patches are gathered from the uint8
     // image inside the kernel; otherwise an im2col pass writes them out first.
     if (parts & 1) {
-        const bool direct = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() >= 3 &&
+        const bool direct = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) &&
                             !c->no_direct_conv1;
         if (!direct) { ProfScope prof(kProfIm2col, st); EAE_TRY(launch_im2col_k9s4(img_dev, A, n, (int)h, (int)w, st)); }
         GemmPlan p = base_plan(A, H1, W1, kIm2colK, c->w1m.as<float>(), c->bias[0].as<float>(), x1, n);
@@ -403,7 +403,7 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
     EAE_TRY(run_tconv5s2(c, x2, H2, W2, c->w5.as<float>(), 4, c->bias[4].as<float>(), x1, 5, n, st));
     // layer 6: conv2d_transpose k9 s4 (128 -> 1), no bias. Kernel version 6 contracts, gathers and casts in one launch;
     // otherwise: per-pixel tap contributions, then col2im.
-    if (c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1) && umma_version() >= 6) {
+    if (c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerThin) & 1)) {
         ProfScope prof(kProfGemmThin, st);
         return launch_tconv9s4_fused(x1, umma_weights(c, 5, 1), out_u8_dev, out_f32_dev, n, (int)h, (int)w, c->exact_now, st);
     }

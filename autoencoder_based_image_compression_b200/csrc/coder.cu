@@ -2,11 +2,11 @@
 // (kodak_tensorflow/lossless/c++/source/{LosslessCoder,BinaryArithmeticCoder,Bitstream}.cpp).
 //
 // Parallel decomposition: the arithmetic coder is strictly sequential inside a stream (one stream =
-// one feature map of one image, compression.py:67-81), so ONE GPU LANE owns one stream and a warp
-// advances 32 streams in lock-step. The encoder's main loop is flattened to "one prefix bin per
-// iteration" so that lanes whose symbols need different numbers of bins stay converged.
-// The split point uses the reference's arithmetic literally: FP64 multiply (round-to-nearest, never
-// fused) followed by floor (BinaryArithmeticCoder.cpp:154).
+// one feature map of one image, compression.py:67-81); everything else is not. A parallel pass (one warp per
+// stream) binarises the symbols and writes the complete bypass stream, then ONE GPU LANE per stream runs the
+// arithmetic coder over the stream's bin string, one branch-free step per bin, 32 streams per warp in lock-step.
+// The split point is the reference's arithmetic: FP64 multiply (round-to-nearest, never fused) followed by floor
+// (BinaryArithmeticCoder.cpp:154), or a fixed-point form proven equal for every range (prepare_table_kernel).
 #include <memory>
 #include <stdlib.h>
 
@@ -18,72 +18,16 @@ namespace eae {
 
 namespace {
 
-// One stream per `lanes` consecutive threads (only the first of them works). lanes = 32 gives every
-// stream its own warp: no divergence and the most warps in flight, which is what a small batch needs
-// because the coder is latency-bound; lanes = 1 packs 32 streams per warp for the best issue efficiency
-// when there are far more streams than warp slots. launch_* pick `lanes` from the stream count.
-__global__ void __launch_bounds__(64, 8)
-encode_streams_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint32_t size,
-                      const double* __restrict__ table, uint32_t table_rows, uint32_t L,
-                      const uint8_t* __restrict__ skip_mask, uint8_t* __restrict__ bac_slots,
-                      uint8_t* __restrict__ byp_slots, uint32_t slot_bytes, uint32_t cap_bits,
-                      uint32_t* __restrict__ bac_bits, uint32_t* __restrict__ byp_bits,
-                      uint32_t* __restrict__ err, uint32_t lanes)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t % lanes) return;
-    const uint32_t s = t / lanes;
-    if (s >= n_streams) return;
-    const uint32_t row = s % table_rows;
-    if (skip_mask && skip_mask[row]) {
-        bac_bits[s] = 0; byp_bits[s] = 0; err[s] = 0;
-        return;
-    }
-    core::BitSink bac, byp;
-    bac.init(bac_slots + (size_t)s * slot_bytes, cap_bits);
-    byp.init(byp_slots + (size_t)s * slot_bytes, cap_bits);
-    const uint32_t e = core::encode_stream(idx + (size_t)s * size, size, table + (size_t)row * L, L, bac, byp);
-    bac.flush();
-    byp.flush();
-    bac_bits[s] = bac.nbits;
-    byp_bits[s] = byp.nbits;
-    err[s] = e;
-}
-
-__global__ void __launch_bounds__(64, 8)
-decode_streams_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
-                      const double* __restrict__ table, uint32_t table_rows, uint32_t L,
-                      const uint8_t* __restrict__ skip_mask, const uint8_t* __restrict__ bac_base,
-                      const uint64_t* __restrict__ bac_off, const uint32_t* __restrict__ bac_bits,
-                      const uint8_t* __restrict__ byp_base, const uint64_t* __restrict__ byp_off,
-                      const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err, uint32_t lanes)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t % lanes) return;
-    const uint32_t s = t / lanes;
-    if (s >= n_streams) return;
-    const uint32_t row = s % table_rows;
-    if (skip_mask && skip_mask[row]) { err[s] = 0; return; }
-    core::BitSource bac, byp;
-    bac.init(bac_base + bac_off[s], bac_bits[s]);
-    byp.init(byp_base + byp_off[s], byp_bits[s]);
-    err[s] = core::decode_stream(out + (size_t)s * size, size, table + (size_t)row * L, L, bac, byp);
-}
-
 // =================================================================================================
-// Coder v2 (default): the lean formulation of coder_core.cuh.
-//
 //   encode = binarize_streams_kernel (parallel: one warp per stream writes the truncated-unary bit string
 //            of the stream and its complete bypass stream)
-//          + encode_streams2_kernel  (sequential: one thread per stream, one branch-light step per bin)
-//   decode = decode_streams2_kernel  (one thread per stream: arithmetic decoding of all prefixes, then the
+//          + encode_streams3_kernel  (sequential: one thread per stream, one branch-free step per bin)
+//   decode = decode_streams3_kernel  (one thread per stream: arithmetic decoding of all prefixes, then the
 //            bypass pass over the same symbols)
 //
-// Version 1 spent ~50 instructions per bin in a warp that carried ONE stream (31 idle lanes), or diverged
-// on every symbol boundary / flush / E3 loop when 32 streams shared a warp. Here the per-bin step has no
-// data-dependent loop and no symbol logic, so the streams of a warp stay converged and the kernel needs
-// ~1/30 of the issue slots: it is bounded by the dependent chain of one step (~100-150 cycles) times the
-// number of bins of the longest stream, and leaves the SMs free for the transforms of other batches.
+// The per-bin step has no data-dependent loop and no symbol logic, so the streams of a warp stay converged: the
+// kernels are bounded by the dependent chain of one step times the number of bins of the longest stream, and leave
+// the SMs free for the transforms of other batches.
 //
 // Streams that share a warp are chosen to be the SAME feature map of different images (similar statistics,
 // hence similar bin counts): slot j -> stream (j % group) * table_rows + j / group.
@@ -171,99 +115,8 @@ __device__ __forceinline__ uint32_t slot_to_stream(uint32_t j, uint32_t group, u
     return group ? (j % group) * table_rows + j / group : j;
 }
 
-__global__ void __launch_bounds__(64)
-encode_streams2_kernel(const uint32_t* __restrict__ nbins, const uint32_t* __restrict__ ubits, uint32_t uwords,
-                       uint32_t n_streams, const double* __restrict__ table, uint32_t table_rows, uint32_t L,
-                       const uint8_t* __restrict__ skip_mask, uint8_t* __restrict__ bac_slots,
-                       uint32_t slot_bytes, uint32_t cap_bits, uint32_t* __restrict__ bac_bits,
-                       uint32_t* __restrict__ err, uint32_t lanes, uint32_t group)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t % lanes) return;
-    const uint32_t j = t / lanes;
-    if (j >= n_streams) return;
-    const uint32_t s = slot_to_stream(j, group, table_rows);
-    const uint32_t row = s % table_rows;
-    if (skip_mask && skip_mask[row]) { bac_bits[s] = 0; err[s] = 0; return; }
-    const double* prow = table + (size_t)row * L;
-    const uint32_t* uw = ubits + (size_t)s * uwords;
-    const uint32_t nb = nbins[s];
-    core::BitSink bac;
-    bac.init(bac_slots + (size_t)s * slot_bytes, cap_bits);
-    core::BacState st = {0u, core::kRangeMax, 0u};
-    uint32_t e = 0, k = 0, w = 0, wnext = nb ? __ldg(uw) : 0u;
-    double p = __ldg(prow);
-    for (uint32_t g = 0; g < nb; g++) {
-        if ((g & 31u) == 0u) {                 // same g for every lane: converged
-            w = wnext;
-            if (g + 32u < nb) wnext = __ldg(uw + (g >> 5) + 1u);
-        }
-        const uint32_t bit = (w >> (g & 31u)) & 1u;
-        k = (bit && k + 1u < L) ? k + 1u : 0u;
-        const double p_next = __ldg(prow + k);  // off the dependent chain of the step below
-        e = core::lean_encode_bin(st, bac, bit, p);
-        if (e) break;
-        p = p_next;
-    }
-    if (!e) e = core::bac_finish(st, bac);
-    bac.flush();
-    bac_bits[s] = bac.nbits;
-    err[s] = e;
-}
-
-__global__ void __launch_bounds__(64)
-decode_streams2_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t size,
-                       const double* __restrict__ table, uint32_t table_rows, uint32_t L,
-                       const uint8_t* __restrict__ skip_mask, const uint8_t* __restrict__ bac_base,
-                       const uint64_t* __restrict__ bac_off, const uint32_t* __restrict__ bac_bits,
-                       const uint8_t* __restrict__ byp_base, const uint64_t* __restrict__ byp_off,
-                       const uint32_t* __restrict__ byp_bits, uint32_t* __restrict__ err, uint32_t lanes,
-                       uint32_t group)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t % lanes) return;
-    const uint32_t j = t / lanes;
-    if (j >= n_streams) return;
-    const uint32_t s = slot_to_stream(j, group, table_rows);
-    const uint32_t row = s % table_rows;
-    if (skip_mask && skip_mask[row]) { err[s] = 0; return; }
-    const double* prow = table + (size_t)row * L;
-    int16_t* dst = out + (size_t)s * size;
-    core::BitSource bac;
-    bac.init(bac_base + bac_off[s], bac_bits[s]);
-    core::DecState st;
-    core::lean_decode_start(st, bac);
-    // phase A: the truncated-unary prefix of every symbol
-    uint32_t e = 0, n_ok = size, i = 0, a = 0, k = 0;
-    const double p0 = __ldg(prow);
-    double p = p0;
-    while (i < size) {
-        if (!(p > 0.0 && p < 1.0)) { e = core::kErrProbability; n_ok = i; break; }
-        // the next probability is p[0] (symbol finished) or p[k + 1]: fetch the latter before the bit is known
-        const double p_up = __ldg(prow + (k + 1u < L ? k + 1u : k));
-        const uint32_t bit = core::lean_decode_bin(st, bac, p);
-        a += bit;
-        const bool done = !bit || k == L - 1u;
-        if (done) { dst[i] = (int16_t)a; i++; a = 0; }
-        k = done ? 0u : k + 1u;
-        p = done ? p0 : p_up;
-    }
-    // phase B: EG0 suffixes and signs from the bypass stream
-    core::BitSource byp;
-    byp.init(byp_base + byp_off[s], byp_bits[s]);
-    for (i = 0; i < n_ok; i++) {
-        const uint32_t a0 = (uint32_t)(uint16_t)dst[i];
-        if (a0 == 0u) continue;
-        int v;
-        const uint32_t eb = core::lean_decode_bypass(a0, L, byp, v);
-        if (eb) { e = eb; break; }
-        dst[i] = (int16_t)v;
-    }
-    err[s] = e;
-}
-
 // =================================================================================================
-// Coder v3 (default): the same two passes with the branch-free step of coder_core.cuh ("fast formulation").
+// The sequential passes: the branch-free step of coder_core.cuh ("fast formulation").
 // Per table row, `row_flags` says whether every probability is valid (bit 0: the loop then needs no error
 // test at all) and whether the 48-bit fixed-point multipliers in `qtable` reproduce floor(p * range) for every
 // range (bit 1, established exhaustively by prepare_table_kernel): rows without bit 0 take the lean loop,
@@ -494,18 +347,7 @@ decode_streams3_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t s
     err[s] = e;
 }
 
-int coder_version()
-{
-    static int v = 0;
-    if (!v) {
-        const char* env = getenv("EAE_CODER_VERSION");
-        v = env ? atoi(env) : 3;
-        if (v < 1 || v > 3) v = 3;
-    }
-    return v;
-}
-
-// Threads per stream slot of the version-2 kernels (only the first thread of a slot works): as few warps as
+// Threads per stream slot of the sequential kernels (only the first thread of a slot works): as few warps as
 // keep about one warp per SM sub-partition busy, so that a small batch still spreads over the whole GPU.
 inline uint32_t lanes_v2(uint32_t n_streams, uint32_t requested)
 {
@@ -518,21 +360,6 @@ inline uint32_t lanes_v2(uint32_t n_streams, uint32_t requested)
     if (requested >= 1 && requested <= 32 && (requested & (requested - 1)) == 0) return requested;
     uint32_t lanes = 32;
     while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 4ull) lanes >>= 1;
-    return lanes;
-}
-
-// Threads per stream: one warp per stream until that would exceed ~32 warps per SM, then halve.
-inline uint32_t lanes_per_stream(uint32_t n_streams, uint32_t requested)
-{
-    static int forced = -1;   // env EAE_CODER_LANES (1, 2, 4, ... 32) overrides the heuristic
-    if (forced < 0) {
-        const char* env = getenv("EAE_CODER_LANES");
-        forced = env ? atoi(env) : 0;
-    }
-    if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0) return (uint32_t)forced;
-    if (requested >= 1 && requested <= 32 && (requested & (requested - 1)) == 0) return requested;
-    uint32_t lanes = 32;
-    while (lanes > 1 && (uint64_t)n_streams * lanes / 32 > 148ull * 32ull) lanes >>= 1;
     return lanes;
 }
 
@@ -654,8 +481,6 @@ static void coder_carveouts()
 {
     static uint64_t seen = 0;
     if (!first_use_on_device(&seen)) return;
-    prefer_max_shared(encode_streams_kernel); prefer_max_shared(decode_streams_kernel);
-    prefer_max_shared(encode_streams2_kernel); prefer_max_shared(decode_streams2_kernel);
     prefer_max_shared(encode_streams3_kernel); prefer_max_shared(decode_streams3_kernel);
     prefer_max_shared(binarize_streams_kernel);
 }
@@ -669,14 +494,6 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
 {
     if (n_streams == 0) return 0;
     coder_carveouts();
-    if (coder_version() == 1) {
-        const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
-        encode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
-            idx_planar, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_slots, byp_slots,
-            slot_bytes, coder_capacity_bits(size, L), bac_bits, byp_bits, err, lanes);
-        EAE_LAUNCH_OK();
-        return 0;
-    }
     void* own = nullptr;
     if (!scratch) {     // callers without a persistent workspace (C-ABI stream entry points)
         EAE_CUDA_OK(cudaMallocAsync(&own, coder_encode_scratch_bytes(n_streams, size, L), st));
@@ -697,12 +514,7 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
     const uint64_t threads = (uint64_t)n_streams * lanes;
     const uint32_t block = coder_block(threads);   // few warps: one per CTA, spread over the SMs
     if (probe_skip() & 2) { if (own) EAE_CUDA_OK(cudaFreeAsync(own, st)); return 0; }
-    if (coder_version() == 2)
-        encode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
-            nbins, ubits, uwords, n_streams, table_dev, table_rows, L, skip_mask_dev, bac_slots, slot_bytes,
-            coder_capacity_bits(size, L), bac_bits, err, lanes, group);
-    else
-        encode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+    encode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
             nbins, ubits, uwords, n_streams, table_dev, qtable_dev, qtable_dev ? row_flags_dev : nullptr, table_rows, L,
             skip_mask_dev, bac_slots, slot_bytes, coder_capacity_bits(size, L), bac_bits, err, lanes, group);
     EAE_LAUNCH_OK();
@@ -719,25 +531,12 @@ int launch_decode_streams(int16_t* idx_planar_out, uint32_t n_streams, uint32_t 
 {
     if (n_streams == 0) return 0;
     coder_carveouts();
-    if (coder_version() == 1) {
-        const uint32_t lanes = lanes_per_stream(n_streams, lanes_req);
-        decode_streams_kernel<<<ceil_div_u32((uint64_t)n_streams * lanes, 64), 64, 0, st>>>(
-            idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off,
-            bac_bits, byp_base, byp_off, byp_bits, err, lanes);
-        EAE_LAUNCH_OK();
-        return 0;
-    }
     const uint32_t lanes = lanes_v2(n_streams, lanes_req);
     const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
     const uint64_t threads = (uint64_t)n_streams * lanes;
     const uint32_t block = coder_block(threads);
     if (probe_skip() & 4) return 0;
-    if (coder_version() == 2)
-        decode_streams2_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
-            idx_planar_out, n_streams, size, table_dev, table_rows, L, skip_mask_dev, bac_base, bac_off, bac_bits,
-            byp_base, byp_off, byp_bits, err, lanes, group);
-    else
-        decode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
+    decode_streams3_kernel<<<ceil_div_u32(threads, block), block, 0, st>>>(
             idx_planar_out, n_streams, size, table_dev, qtable_dev, qtable_dev ? row_flags_dev : nullptr, table_rows, L,
             skip_mask_dev, bac_base, bac_off, bac_bits, byp_base, byp_off, byp_bits, err, lanes, group);
     EAE_LAUNCH_OK();

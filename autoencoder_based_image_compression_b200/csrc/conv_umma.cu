@@ -23,7 +23,7 @@
 #include "common.cuh"
 #include "conv_plan.cuh"
 #include "transforms.cuh"
-#include "umma_last_layer.cuh"      // pulls in umma_common / v1 ... v5 in order
+#include "umma_last_layer.cuh"      // pulls in umma_common / v3 / v4
 
 namespace eae {
 
@@ -118,17 +118,6 @@ int umma_check_error(cudaStream_t st)
     return 0;
 }
 
-int umma_version()
-{
-    static int v = 0;
-    if (!v) {
-        const char* env = getenv("EAE_UMMA_VERSION");
-        v = env ? atoi(env) : 7;
-        if (v < 1 || v > 7) v = 7;
-    }
-    return v;
-}
-
 int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeights* gamma, bool exact3x,
                      cudaStream_t st, const GemmPlan* more, int n_more)
 {
@@ -182,9 +171,9 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
     if (plan.img_u8) {
-        if (umma_version() < 3 || plan.n_taps != 1 || plan.Cin != 96 || plan.Hg * 4 != plan.img_H ||
+        if (plan.n_taps != 1 || plan.Cin != 96 || plan.Hg * 4 != plan.img_H ||
             plan.Wg * 4 != plan.img_W || plan.img_W % 16 != 0) {
-            set_error("gemm_umma: the fused k9 s4 convolution needs kernel version 3 and a [n, 4 Hg, 4 Wg] image");
+            set_error("gemm_umma: the fused k9 s4 convolution needs a 1-tap plan and a [n, 4 Hg, 4 Wg] image");
             return EAE_ERR_ARGUMENT;
         }
         map_a = map_b_hi;      // not read
@@ -250,7 +239,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         return true;
     };
     auto eligible4 = [&](const GemmPlan& pl) {
-        return umma_version() >= 4 && pl.n_taps > 1 && pl.n_taps <= kMaxTaps && pl.Hg > 1 && pl.Cin == 128 && !pl.img_u8 &&
+        return pl.n_taps > 1 && pl.n_taps <= kMaxTaps && pl.Hg > 1 && pl.Cin == 128 && !pl.img_u8 &&
                pl.in == plan.in && pl.Hg == plan.Hg && pl.Wg == plan.Wg && pl.in_split == plan.in_split && pl.M == plan.M &&
                pl.fuse == plan.fuse && pl.fuse_single_pass == plan.fuse_single_pass;
     };
@@ -339,76 +328,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             return 0;
         }
     }
-    // Version 5 pays off for the thin layers WITHOUT a fused GDN (the last layer: 195 -> 152 us per 24 images); with the
-    // fused tail (layer 1) two half-size CTAs contend for the tensor pipe and shared-memory bandwidth of the GDN steps and
-    // the single GDN stage serialises them: 290 us against 250 us on version 3 (EAE_UMMA_V5_FUSED=1 routes it here anyway).
-    static int v5_fused = -1;
-    if (v5_fused < 0) { const char* e = getenv("EAE_UMMA_V5_FUSED"); v5_fused = e ? atoi(e) : 0; }
-    if (umma_version() >= 5 && plan.n_taps == 1 && p.tile_h == 8 && plan.mode == kEpiBias && p.taps[0].fy == 0 &&
-        p.taps[0].fx == 0 && p.taps[0].plane == 0 && (plan.img_u8 ? plan.Cin == 96 : true) && (!plan.fuse || v5_fused)) {
-        // ---- version 5: thin layers, 128 positions per CTA, two CTAs per SM ----
-        UmmaParams5 q;
-        memset(&q, 0, sizeof q);
-        q.kchunks = plan.Cin / kChunkK;
-        q.conv1 = plan.img_u8 ? 1 : 0;
-        q.tiles_x = (plan.Wg + 15) / 16; q.tiles_y = (plan.Hg + 7) / 8;
-        q.Hg = plan.Hg; q.Wg = plan.Wg;
-        q.out = plan.out; q.bias = plan.bias; q.beta = plan.fuse_beta;
-        q.Hout = plan.Hout; q.Wout = plan.Wout; q.out_mul = plan.out_mul; q.out_r = plan.out_r; q.out_s = plan.out_s;
-        q.out_split = plan.out_split;
-        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0;
-        q.error_flag = g_error_flag;
-        CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo, map_img = map_b_hi;
-        if (plan.fuse) {
-            if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta) {
-                set_error("gemm_umma: fused GDN needs gamma hi/lo and beta");
-                return EAE_ERR_ARGUMENT;
-            }
-            const uint64_t gdims[3] = {kCout, kCout, 1};
-            EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
-            EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
-        }
-        if (plan.img_u8) EAE_TRY(make_map_u8(&map_img, plan.img_u8, (uint64_t)plan.img_W, (uint64_t)plan.img_H, n_img));
-        static bool attr5_done = false;
-        if (!attr5_done) {
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes5));
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma5_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr5_done = true;
-        }
-        const uint32_t grid5 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
-        if (getenv("EAE_UMMA_TIMING") && atoi(getenv("EAE_UMMA_TIMING")) == 1) {
-            // Debug: which SM ran each CTA and when; prints the largest number of CTAs alive at once on one SM.
-            long long* d_times = nullptr;
-            EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid5 * 3 * sizeof(long long)));
-            q.times = d_times;
-            gemm_umma5_kernel<<<grid5, kThreads5, kSmemBytes5, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
-            EAE_LAUNCH_OK();
-            std::vector<long long> h((size_t)grid5 * 3);
-            EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
-            EAE_CUDA_OK(cudaStreamSynchronize(st));
-            cudaFree(d_times);
-            int worst = 0;
-            double mean_ns = 0.;
-            long long t_min = h[1], t_max = h[2];
-            for (uint32_t b = 0; b < grid5; b++) {
-                int alive = 0;
-                for (uint32_t c = 0; c < grid5; c++)
-                    if (h[(size_t)c * 3] == h[(size_t)b * 3] && h[(size_t)c * 3 + 1] <= h[(size_t)b * 3 + 1] && h[(size_t)c * 3 + 2] > h[(size_t)b * 3 + 1]) alive++;
-                if (alive > worst) worst = alive;
-                mean_ns += (double)(h[(size_t)b * 3 + 2] - h[(size_t)b * 3 + 1]);
-                if (h[(size_t)b * 3 + 1] < t_min) t_min = h[(size_t)b * 3 + 1];
-                if (h[(size_t)b * 3 + 2] > t_max) t_max = h[(size_t)b * 3 + 2];
-            }
-            fprintf(stderr, "umma5 conv1 %d fuse %d grid %u: up to %d CTAs alive on one SM, mean CTA %.1f us, kernel %.1f us\n", q.conv1,
-                    q.fuse, grid5, worst, mean_ns / grid5 * 1e-3, (double)(t_max - t_min) * 1e-3);
-            return 0;
-        }
-        gemm_umma5_kernel<<<grid5, kThreads5, kSmemBytes5, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
-        EAE_LAUNCH_OK();
-        return 0;
-    }
-    if (umma_version() >= 3) {
-        UmmaParams2 q;
+    {
+        UmmaParams3 q;
         memset(&q, 0, sizeof q);
         q.n_taps = p.n_taps; q.kchunks = p.kchunks;
         q.tile_w = p.tile_w; q.tile_h = p.tile_h;
@@ -424,11 +345,9 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.fuse = plan.fuse;
         q.exact_main = exact3x ? 1 : 0;
         q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
-        q.cluster = 1;
         q.error_flag = p.error_flag;
         memcpy(q.taps, p.taps, sizeof q.taps);
         const uint32_t grid3 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
-        q.n_tiles = (int)grid3;
         CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo, map_img = map_b_hi;
         if (plan.fuse) {
             if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias || p.tile_h == 1) {
@@ -480,85 +399,6 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         EAE_LAUNCH_OK();
         return 0;
     }
-    if (umma_version() == 2) {
-        // Cluster size: B tiles are identical for every CTA, so the CTAs of a cluster split each B tile and
-        // multicast their slices (env EAE_UMMA_CLUSTER: 1, 2 or 4; default 2 when there are enough tiles).
-        static int cs_env = -1;
-        if (cs_env < 0) { const char* env = getenv("EAE_UMMA_CLUSTER"); cs_env = env ? atoi(env) : 0; }
-        unsigned cs = (cs_env == 1 || cs_env == 2 || cs_env == 4) ? (unsigned)cs_env : 2u;
-        if (grid < 2 * cs) cs = 1;
-        if (cs > 1) {
-            const uint32_t sbox[3] = {kChunkK, kCout / cs, 1};
-            EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, sbox));
-            EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, sbox));
-        }
-        UmmaParams2 q;
-        memset(&q, 0, sizeof q);
-        q.cluster = (int)cs;
-        q.n_tiles = (int)grid;
-        { static int dbg = -1; if (dbg < 0) { const char* e = getenv("EAE_UMMA_DEBUG"); dbg = e ? atoi(e) : 0; } q.debug = dbg; }
-        q.n_taps = p.n_taps; q.kchunks = p.kchunks;
-        q.tile_w = p.tile_w; q.tile_h = p.tile_h; q.tiles_x = p.tiles_x; q.tiles_y = p.tiles_y;
-        q.Hg = p.Hg; q.Wg = p.Wg;
-        q.out = p.out; q.bias = p.bias; q.beta = plan.fuse_beta; q.xin = p.xin;
-        q.Hout = p.Hout; q.Wout = p.Wout; q.out_mul = p.out_mul; q.out_r = p.out_r; q.out_s = p.out_s;
-        q.out_split = p.out_split;
-        q.mode = p.mode;
-        q.fuse = plan.fuse;
-        q.exact_main = exact3x ? 1 : 0;
-        q.error_flag = p.error_flag;
-        memcpy(q.taps, p.taps, sizeof q.taps);
-        CUtensorMap map_g_hi = map_b_hi, map_g_lo = map_b_lo;
-        if (plan.fuse) {
-            if (!gamma || !gamma->hi || !gamma->lo || !plan.fuse_beta || plan.mode != kEpiBias) {
-                set_error("gemm_umma: fused GDN needs gamma hi/lo, beta and a bias-mode contraction");
-                return EAE_ERR_ARGUMENT;
-            }
-            const uint64_t gdims[3] = {kCout, kCout, 1};
-            const uint32_t gbox[3] = {kChunkK, kCout / cs, 1};
-            EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, gbox));
-            EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, gbox));
-        }
-        static bool attr2_done = false;
-        if (!attr2_done) {
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-            attr2_done = true;
-        }
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(((grid + cs - 1) / cs) * cs);
-        cfg.blockDim = dim3(kUmmaThreads2);
-        cfg.dynamicSmemBytes = kSmemBytes2;
-        cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        EAE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_umma2_kernel, map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, q));
-        EAE_LAUNCH_OK();
-        return 0;
-    }
-    if (plan.fuse) { set_error("gemm_umma: fused GDN needs kernel version 2 or 3"); return EAE_ERR_ARGUMENT; }
-    if (exact3x) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<true>::kSmemBytes));
-            attr_done = true;
-        }
-        gemm_umma_kernel<true><<<grid, kUmmaThreads, Cfg<true>::kSmemBytes, st>>>(map_a, map_b_hi, map_b_lo, p);
-    } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg<false>::kSmemBytes));
-            attr_done = true;
-        }
-        gemm_umma_kernel<false><<<grid, kUmmaThreads, Cfg<false>::kSmemBytes, st>>>(map_a, map_b_hi, map_b_lo, p);
-    }
-    EAE_LAUNCH_OK();
-    return 0;
 }
 
 int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
@@ -576,15 +416,8 @@ int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8
         EAE_CUDA_OK(cudaMemset(g_error_flag, 0, 4));
     }
     const int H1 = H / 4, W1 = W / 4;
-    UmmaParams6 q;
-    memset(&q, 0, sizeof q);
-    q.kchunks = kCout / kChunkK;
-    q.tiles_y = (H1 + 1 + kBlkY6 - 1) / kBlkY6;      // pixel blocks 0 .. H1 (the first and the last are half blocks)
-    q.tiles_x = (W1 + 1 + kBlkX6 - 1) / kBlkX6;
-    q.H = H; q.W = W;
-    q.out_u8 = out_u8; q.out_f32 = out_f32;
-    q.exact_main = exact3x ? 1 : 0;
-    q.error_flag = g_error_flag;
+    const int tiles_y = (H1 + 1 + kBlkY6 - 1) / kBlkY6;      // pixel blocks 0 .. H1 (the first and the last are half blocks)
+    const int tiles_x = (W1 + 1 + kBlkX6 - 1) / kBlkX6;
     CUtensorMap map_a, map_b_hi, map_b_lo;
     const uint64_t adims[5] = {(uint64_t)kCout, (uint64_t)W1, (uint64_t)H1, 1, n};
     const uint32_t abox[5] = {kChunkK, 16, 8, 1, 1};
@@ -593,38 +426,25 @@ int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8
     const uint32_t bbox[3] = {kChunkK, 96, 1};
     EAE_TRY(make_map(&map_b_hi, w.hi, 3, bdims, bbox));
     EAE_TRY(make_map(&map_b_lo, exact3x ? w.lo : w.hi, 3, bdims, bbox));
-    if (umma_version() >= 7) {
-        UmmaParams7 q7;
-        memset(&q7, 0, sizeof q7);
-        q7.tiles_x = q.tiles_x; q7.tiles_y = q.tiles_y;
-        const uint64_t n_tiles = (uint64_t)n * (uint64_t)(q.tiles_x * q.tiles_y);
-        if (n_tiles >= (1ull << 31)) { set_error("tconv9s4: batch too large"); return EAE_ERR_ARGUMENT; }
-        q7.n_tiles = (int)n_tiles;
-        q7.H = H; q7.W = W;
-        q7.out_u8 = out_u8; q7.out_f32 = out_f32;
-        q7.exact_main = q.exact_main;
-        q7.error_flag = g_error_flag;
-        static int n_sms = 0;
-        if (!n_sms) {
-            int dev = 0;
-            EAE_CUDA_OK(cudaGetDevice(&dev));
-            EAE_CUDA_OK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-            EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes7));
-        }
-        const uint32_t grid7 = n_tiles < (uint64_t)n_sms ? (uint32_t)n_tiles : (uint32_t)n_sms;
-        tconv9s4_umma7_kernel<<<grid7, kThreads7, kSmemBytes7, st>>>(map_a, map_b_hi, map_b_lo, q7);
-        EAE_LAUNCH_OK();
-        return 0;
+    UmmaParams7 q7;
+    memset(&q7, 0, sizeof q7);
+    q7.tiles_x = tiles_x; q7.tiles_y = tiles_y;
+    const uint64_t n_tiles = (uint64_t)n * (uint64_t)(tiles_x * tiles_y);
+    if (n_tiles >= (1ull << 31)) { set_error("tconv9s4: batch too large"); return EAE_ERR_ARGUMENT; }
+    q7.n_tiles = (int)n_tiles;
+    q7.H = H; q7.W = W;
+    q7.out_u8 = out_u8; q7.out_f32 = out_f32;
+    q7.exact_main = exact3x ? 1 : 0;
+    q7.error_flag = g_error_flag;
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        EAE_CUDA_OK(cudaGetDevice(&dev));
+        EAE_CUDA_OK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes7));
     }
-    static bool attr6_done = false;
-    if (!attr6_done) {
-        EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes6));
-        EAE_CUDA_OK(cudaFuncSetAttribute(tconv9s4_umma6_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr6_done = true;
-    }
-    const uint64_t grid = (uint64_t)n * (uint64_t)(q.tiles_x * q.tiles_y);
-    if (grid >= (1ull << 31)) { set_error("tconv9s4: batch too large"); return EAE_ERR_ARGUMENT; }
-    tconv9s4_umma6_kernel<<<(uint32_t)grid, kThreads5, kSmemBytes6, st>>>(map_a, map_b_hi, map_b_lo, q);
+    const uint32_t grid7 = n_tiles < (uint64_t)n_sms ? (uint32_t)n_tiles : (uint32_t)n_sms;
+    tconv9s4_umma7_kernel<<<grid7, kThreads7, kSmemBytes7, st>>>(map_a, map_b_hi, map_b_lo, q7);
     EAE_LAUNCH_OK();
     return 0;
 }

@@ -28,9 +28,6 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
 // K-major tap matrix `w` ([128 tap columns, 81 used][128 in]) + the col2im gather + the BT.601 cast / float output.
 int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
                           bool exact3x, cudaStream_t st);
-// 1: operands from shared memory, no fusion; 2: A in TMEM, GDN / IGDN fusable; 3 (default): 2 + 256 rows per CTA
-// and a coalesced epilogue (env EAE_UMMA_VERSION).
-int umma_version();
 // Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
 int umma_check_error(cudaStream_t st);
 // The device word behind umma_check_error (NULL before the first tensor-path launch); kernels may read and clear it.

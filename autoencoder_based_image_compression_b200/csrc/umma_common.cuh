@@ -1,4 +1,4 @@
-// Constants, parameter blocks and PTX wrappers shared by every generation of the tcgen05 tap-list GEMM (conv_umma.cu).
+// Constants, parameter blocks and PTX wrappers shared by the tcgen05 kernels (conv_umma.cu).
 // Private to conv_umma.cu (one translation unit): everything here sits in its anonymous namespace.
 #pragma once
 
@@ -15,18 +15,8 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int kTileBytes = kTileM * 128;    // 16 KB: 128 rows x 128 bytes
-constexpr int kUmmaThreads = 192;           // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue / A split
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols2 = 512;              // every kernel here owns the whole TMEM of its SM (one CTA per SM)
 constexpr long long kTimeoutCycles = 400ll * 1000 * 1000;   // ~0.2 s
-
-template <bool kExact> struct Cfg {
-    static constexpr int kStageBytes = kExact ? 4 * kTileBytes : 2 * kTileBytes;   // A [A_lo] B [B_lo]
-    static constexpr int kStages = kExact ? 3 : 6;
-    static constexpr int kOffAlo = kTileBytes;
-    static constexpr int kOffBhi = kExact ? 2 * kTileBytes : kTileBytes;
-    static constexpr int kOffBlo = 3 * kTileBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
-};
 
 struct UmmaTap { int plane, fy, fx, w_tap; };
 
@@ -148,6 +138,57 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Parameters of gemm_umma3_kernel (layer 1 and the standalone GDN / IGDN).
+struct UmmaParams3 {
+    int n_taps, kchunks;
+    int tile_w, tile_h, tiles_x, tiles_y;
+    int Hg, Wg;
+    float* out;
+    const float* bias;
+    const float* beta;       // fused GDN / IGDN
+    const float* xin;        // standalone GDN / IGDN: the un-squared input
+    int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int mode;                // EpilogueMode of a standalone launch
+    int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
+    int exact_main;          // 3xTF32 for the main contraction
+    int exact_gdn;           // 3xTF32 for the fused norm (versions 3 and 4)
+    int tile_w_log2;
+    int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
+    int conv1;               // version 3: A rows are the 9x9 patches (k9 s4) of a uint8 image tile staged by TMA
+    long long* times;        // version 3, env EAE_UMMA_TIMING=1: [grid][8] clock64 stamps of the phases of each CTA
+    uint32_t* error_flag;
+    UmmaTap taps[kMaxTaps];
+};
+
+
+// A operand from tensor memory, B from shared memory.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+                 :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr) : "memory");
 }
 
 }  // namespace

@@ -1,20 +1,19 @@
-// Versions 6 and 7: the last layer (transposed k9 s4 convolution) with its col2im gather and the BT.601 cast in the kernel.
+// The last layer (transposed k9 s4 convolution) with its col2im gather and the BT.601 cast in the kernel.
 // Private to conv_umma.cu (one translation unit): everything here sits in its anonymous namespace.
 #pragma once
 
-#include "umma_v5.cuh"
+#include "umma_v4.cuh"
 
 namespace eae {
 namespace {
 
 // =================================================================================================
-// Version 6: the LAST layer (conv2d_transpose k9 s4, 128 -> 1, components.py:79-84) with its col2im gather and the
+// The LAST layer (conv2d_transpose k9 s4, 128 -> 1, components.py:79-84) with its col2im gather and the
 // BT.601 cast (tools.py:61-93) inside the kernel.
 //
-// Measured on version 5 (profiles/r01_ncu_full_gemm_layers_final.md): the per-position tap matrix [positions, 128] is
+// Measured on the first tensor version of this layer (profiles/r01_ncu_full_gemm_layers_final.md): the per-position tap matrix [positions, 128] is
 // written to HBM (257 MB per 24 images) only to be read back by col2im_k9s4_kernel (another 302 MB + 94 us), for 9 MB
-// of pixels. Here a CTA contracts a tile of 8 x 16 positions (as version 5: thread = position = TMEM lane, two CTAs
-// per SM), dumps the 81 tap columns of its accumulator to shared memory and gathers the pixels of the 6 x 14 pixel
+// of pixels. Here a CTA contracts tiles of 8 x 16 positions (thread = position = TMEM lane), dumps the 81 tap columns of its accumulator to shared memory and gathers the pixels of the 6 x 14 pixel
 // blocks whose contributing positions all lie inside the tile: pixel row oy = 4 q + r - 2 (block q, r in [0, 4))
 // receives position q through ky = r, q - 1 through ky = r + 4 and, for r = 0, q - 2 through ky = 8 - so blocks
 // [q0, q0 + 6) need positions [q0 - 2, q0 + 6). Tiles overlap by two positions (65 % of the contracted rows are
@@ -23,19 +22,7 @@ namespace {
 // MMA N = 96 (81 taps used). HBM traffic: the activations once (the overlap is served by L2) + the pixels.
 constexpr int kColStride6 = 87;                    // odd: the thread-per-row dump is conflict-free
 constexpr int kBlkY6 = 6, kBlkX6 = 14;             // pixel blocks (4 x 4 pixels) a tile completes
-constexpr int kSmemBytes6 = kMainBytes5 + 256 + 1024;
 constexpr uint32_t kInstrDescN96 = (1u << 4) | (2u << 7) | (2u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
-static_assert(kTileM * kColStride6 * 4 <= kMainBytes5, "tap columns alias the stages");
-
-struct UmmaParams6 {
-    int kchunks;
-    int tiles_x, tiles_y;
-    int H, W;                // output image
-    uint8_t* out_u8;         // [n, H, W] or NULL
-    float* out_f32;          // [n, H, W] un-clipped, or NULL
-    int exact_main;
-    uint32_t* error_flag;
-};
 
 __device__ __forceinline__ void umma_tf32_ts_n96(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate)
 {
@@ -47,183 +34,10 @@ __device__ __forceinline__ void umma_tf32_ts_n96(uint32_t tmem_d, uint32_t tmem_
         : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2)
-tconv9s4_umma6_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_hi,
-                      const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ UmmaParams6 p)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMainBytes5);
-    uint64_t* full = bars;                 // [2] stage landed
-    uint64_t* done = bars + 2;             // [2] MMAs of the iteration that used the stage completed
-    uint64_t* split = bars + 4;            // [2] TMEM A slot written (one arrival per conversion warp)
-    uint64_t* acc_full = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
-    const int q0 = (trem / p.tiles_x) * kBlkY6, p0 = (trem % p.tiles_x) * kBlkX6;      // first pixel block of the tile
-    const int a0 = q0 - 2, b0 = p0 - 2;                                                // first position of the tile
-    constexpr int kStageBytes = 3 * kTileBytes;                                         // A | B_hi | B_lo
-    const int n_main = p.kchunks;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&done[s], 1); mbar_init(&split[s], 4); }
-        mbar_init(acc_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols5) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;      // 0 or 256: two CTAs share the SM
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            bool ok = true;
-            for (int it = 0; it < n_main && ok; it++) {
-                const int s = it & 1;
-                if (it >= 2) ok = mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u, p.error_flag, 0);
-                if (!ok) break;
-                uint8_t* st = smem + s * kStageBytes;
-                mbar_expect_tx(&full[s], kTileBytes + (p.exact_main ? 2 : 1) * 96 * 128);
-                tma_load_5d(st, &map_a, &full[s], it * kChunkK, b0, a0, 0, img);        // rows outside the input: zeros
-                tma_load_3d(st + kTileBytes, &map_b_hi, &full[s], it * kChunkK, 0, 0);
-                if (p.exact_main) tma_load_3d(st + 2 * kTileBytes, &map_b_lo, &full[s], it * kChunkK, 0, 0);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
-        const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
-        bool ok = true;
-        for (int it = 0; it < n_main && ok; it++) {
-            const int s = it & 1;
-            ok = __all_sync(0xFFFFFFFFu, mbar_wait(&split[s], (uint32_t)(it >> 1) & 1u, p.error_flag, 1));
-            if (!ok) break;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint32_t st = smem_u32(smem + s * kStageBytes + kTileBytes);
-                const uint32_t a_hi = tb + kCol5Slots + 64u * (uint32_t)s, a_lo = a_hi + 32u;
-                #pragma unroll
-                for (int k = 0; k < kChunkK / 8; k++) {
-                    const uint64_t b_hi = make_desc(st + k * 32);
-                    umma_tf32_ts_n96(tb, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
-                    if (p.exact_main) {
-                        umma_tf32_ts_n96(tb, a_lo + 8 * k, b_hi, 1u);
-                        umma_tf32_ts_n96(tb, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
-                    }
-                }
-                umma_commit(&done[s]);
-                if (it == n_main - 1) umma_commit(acc_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== warps 2..5: operand conversion, then the gather (thread = position = accumulator row = TMEM lane) =====
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        bool ok = true;
-        uint32_t r[32];
-        for (int it = 0; it < n_main && ok; it++) {
-            const int s = it & 1;
-            ok = mbar_wait(&full[s], (uint32_t)(it >> 1) & 1u, p.error_flag, 2);
-            if (!ok) break;
-            const uint8_t* rowp = smem + s * kStageBytes + row * 128;
-            #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (row & 7)) << 4));
-                r[4 * c + 0] = __float_as_uint(v.x); r[4 * c + 1] = __float_as_uint(v.y);
-                r[4 * c + 2] = __float_as_uint(v.z); r[4 * c + 3] = __float_as_uint(v.w);
-            }
-            if (it >= 2) {      // the MMAs of iteration it - 2 read this TMEM slot
-                ok = mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u, p.error_flag, 5);
-                if (!ok) break;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            const uint32_t slot = lane_base + kCol5Slots + 64u * (uint32_t)s;
-            if (!p.exact_main) {      // single pass: round to nearest TF32 (see version 4)
-                #pragma unroll
-                for (int i = 0; i < 32; i++) r[i] += 0x1000u;
-            }
-            tmem_st32(slot, r);
-            if (p.exact_main) {
-                #pragma unroll
-                for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) - __uint_as_float(r[i] & 0xFFFFE000u));
-                tmem_st32(slot + 32u, r);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&split[s]);
-        }
-        if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- tap columns of this position -> shared memory (every MMA, hence every read of the stages, has completed)
-        float* col = reinterpret_cast<float*>(smem);
-        {
-            float* mine = col + row * kColStride6;
-            tmem_ld32(lane_base, r);
-            #pragma unroll
-            for (int i = 0; i < 32; i++) mine[i] = __uint_as_float(r[i]);
-            tmem_ld32(lane_base + 32u, r);
-            #pragma unroll
-            for (int i = 0; i < 32; i++) mine[32 + i] = __uint_as_float(r[i]);
-            tmem_ld32(lane_base + 64u, r);
-            #pragma unroll
-            for (int i = 0; i < 17; i++) mine[64 + i] = __uint_as_float(r[i]);
-        }
-        named_bar_sync(1, 128);
-        // ---- gather: one item = two horizontally adjacent pixels (s0, s0 + 1) of pixel block (qa, pb), row r
-        const int t = threadIdx.x - 64;
-        #pragma unroll 1
-        for (int item = t; item < 4 * kBlkY6 * 2 * kBlkX6; item += 128) {
-            const int ly = item / (2 * kBlkX6), pr = item - ly * (2 * kBlkX6);
-            const int qa = ly >> 2, rr = ly & 3;
-            const int pb = pr >> 1, s0 = (pr & 1) * 2;
-            const int oy = 4 * (q0 + qa) + rr - 2, ox = 4 * (p0 + pb) + s0 - 2;
-            if (!ok || oy < 0 || oy >= p.H || ox < 0 || ox >= p.W) continue;
-            float acc0 = 0.f, acc1 = 0.f;
-            #pragma unroll
-            for (int da = 0; da < 3; da++) {
-                const int ky = rr + 4 * da;
-                if (ky > 8) continue;
-                const float* rowc = col + ((qa + 2 - da) * 16 + pb + 2) * kColStride6 + ky * 9 + s0;
-                #pragma unroll
-                for (int db = 0; db < 3; db++) {
-                    const float* c = rowc - db * kColStride6 + 4 * db;      // position pb + 2 - db, tap kx = s0 + 4 db
-                    if (s0 + 4 * db <= 8) acc0 += c[0];
-                    if (s0 + 4 * db + 1 <= 8) acc1 += c[1];
-                }
-            }
-            const size_t at = ((size_t)img * p.H + oy) * p.W + ox;
-            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + at) = make_float2(acc0, acc1);
-            if (p.out_u8) {
-                uchar2 v;
-                v.x = (uint8_t)(int)rintf(fminf(fmaxf(acc0, 16.f), 235.f));
-                v.y = (uint8_t)(int)rintf(fminf(fmaxf(acc1, 16.f), 235.f));
-                *reinterpret_cast<uchar2*>(p.out_u8 + at) = v;
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols5) : "memory");
-    }
-}
-
 // =================================================================================================
-// Version 7: version 6 as a PERSISTENT, fully pipelined kernel (one CTA per SM, tiles round-robin).
+// The kernel is PERSISTENT and fully pipelined (one CTA per SM, tiles round-robin).
 //
-// Measured on version 6 (two 128-position CTAs per SM): 170 us per 24 images = 13 k cycles per CTA, of which the
+// Measured on a one-tile-per-CTA version (two 128-position CTAs per SM): 170 us per 24 images = 13 k cycles per CTA, of which the
 // tensor pipe needs 2.3 k (3xTF32) and shared-memory / L2 bandwidth less - the time is the serial chain TMEM
 // allocation -> first TMA round trip -> 4 x (convert -> MMA) -> dump -> gather -> stores of every CTA, and each CTA
 // re-fetches the 96 KB of split weights from L2. Here the weights are loaded ONCE per SM and stay in shared memory,
