@@ -54,6 +54,12 @@ class BatchStats(ctypes.Structure):
     _fields_ = [('bits_per_map', u64*EAE_NB_MAPS), ('total_bits', u64), ('nb_dead_maps', u64)]
 
 
+class CodecStatus(ctypes.Structure):
+    """``eae_codec_status_t``."""
+    _fields_ = [('int16_overflow', u32), ('container_overflow', u32), ('container_invalid', u32), ('coder_error', u32),
+                ('tensor_timeout_mask', u32)]
+
+
 # name -> (restype, argtypes). Every symbol declared in include/eae_b200.h is listed here and
 # tests/test_abi.py checks the two against each other.
 PROTOTYPES = {
@@ -121,7 +127,9 @@ PROTOTYPES = {
     'eae_decompress_host': (c_int, [c_void_p, P(CodingParams), c_void_p, u64, c_void_p, u64, c_void_p]),
     'eae_compress_dev': (c_int, [c_void_p, P(CodingParams), c_void_p, u32, u32, u32, c_void_p, u64, c_void_p,
                                  c_void_p, c_void_p]),
-    'eae_decompress_dev': (c_int, [c_void_p, P(CodingParams), c_void_p, u32, u32, u32, c_void_p, c_void_p]),
+    'eae_decompress_dev': (c_int, [c_void_p, P(CodingParams), c_void_p, u64, u32, u32, u32, c_void_p, c_void_p]),
+    'eae_codec_poll_status': (c_int, [c_void_p, c_void_p, P(CodecStatus)]),
+    'eae_debug_check_norm_arithmetic': (c_int, [u64, P(u64), P(u64)]),
     'eae_last_indices_host': (c_int, [c_void_p, c_void_p, u64]),
 }
 

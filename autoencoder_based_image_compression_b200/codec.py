@@ -193,6 +193,17 @@ class Codec(object):
                                                         _native.ptr(out), out.size, self.stream))
         return out
 
+    def poll_status(self, raise_on_error=True):
+        """What the device-resident steps (``eae_compress_dev`` / ``eae_decompress_dev``) of this codec recorded since the
+        previous poll; waits for the codec's stream. Returns a dict; raises like the host entry points would have."""
+        status = _native.CodecStatus()
+        code = _native.lib().eae_codec_poll_status(self.handle, self.stream, ctypes.byref(status))
+        out = {name: int(getattr(status, name)) for (name, _) in _native.CodecStatus._fields_}
+        out['code'] = int(code)
+        if raise_on_error:
+            _native.check(code)
+        return out
+
     def last_indices(self, n, h, w):
         """int16 [n, 128, h/16 * w/16] produced by the last compress / decompress (parity hook)."""
         out = numpy.empty((n, 128, (h//16)*(w//16)), dtype=numpy.int16)

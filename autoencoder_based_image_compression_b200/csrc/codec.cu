@@ -42,6 +42,8 @@ struct eae_codec {
     uint32_t coder_lanes = 0;   // threads per coded stream: 0 = auto (one warp per stream while they fit: lowest latency)
     int no_fuse = 0;       // debug: env EAE_NO_FUSE=1 keeps GDN / IGDN as separate launches
     int no_direct_conv1 = 0;   // debug: env EAE_NO_DIRECT_CONV1=1 keeps the im2col pass in front of layer 1
+    int no_fuse_quant = 0;     // debug: env EAE_NO_FUSE_QUANT=1 keeps the quantizer / dequantizer as separate launches
+    int gdn_precise = 2;       // env EAE_GDN_PRECISE: see run_layer
     // The four output phases of a transposed convolution as ONE grid: 40 us less per 24-image step when the transforms run
     // alone (the phases of a tile share their input box in L2, six dependent launches disappear). With 16 pipeline slots it
     // wins 1.6 % when the step is replayed as a graph (1.59 vs 1.615 ms per step) and loses 3 % when it is launched kernel
@@ -88,6 +90,9 @@ struct eae_codec {
     uint64_t last_idx_elems = 0;
     // pinned, device-visible result block of the _host entry points: one kernel writes it, one synchronisation reads it
     struct HostMailbox* mailbox = nullptr;
+    void* status_host = nullptr;          // pinned HostStatus of eae_codec_poll_status
+    cudaStream_t last_stream = nullptr;   // stream of the last compress / decompress step
+    uint32_t last_n_streams = 0;
 };
 
 struct HostMailbox {
@@ -177,7 +182,8 @@ int ensure_coder(eae_codec* c, uint32_t n_streams, uint32_t size, uint32_t L)
     EAE_TRY(c->byp_off.alloc((size_t)n_streams * 8));
     EAE_TRY(c->enc_scratch.alloc(coder_encode_scratch_bytes(n_streams, size, L)));
     if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
-    if (!c->flag.p) EAE_TRY(c->flag.alloc(8));   // [0] bit flags, [1] first coder error
+    // [0] bit flags of the step (int16 overflow), [1] first coder error of the step, [2] [3] sticky status (kStatus*)
+    if (!c->flag.p) { EAE_TRY(c->flag.alloc(16)); EAE_CUDA_OK(cudaMemset(c->flag.p, 0, 16)); }
     if (!c->stats.p) EAE_TRY(c->stats.alloc(sizeof(eae_batch_stats_t)));
     c->cw_streams = n_streams; c->cw_size = size; c->cw_L = L; c->cw_slot = slot;
     c->generation++;
@@ -278,10 +284,15 @@ UmmaWeights umma_weights(eae_codec* c, int layer, int n_taps)
 
 // GDN / IGDN as a 1-tap contraction with the squared input (tfutils.py:393-397, 506-509). Pixel-wise,
 // hence indifferent to the storage order of the pixels: the plan is a flat [n_pixels, 128] matrix.
-int run_gdn(eae_codec* c, const float* in, float* out, uint32_t n_pixels, int which, bool inverse, cudaStream_t st)
+// dq (IGDN on the tensor path only): the input is the dequantized planar indices instead of `in` (conv_plan.cuh).
+struct DequantIn { const int16_t* idx; const float* mean; const float* delta; int hw; };
+
+int run_gdn(eae_codec* c, const float* in, float* out, uint32_t n_pixels, int which, bool inverse, cudaStream_t st,
+            const DequantIn* dq = nullptr)
 {
     GemmPlan p = base_plan(in, 1, (int)n_pixels, 128, c->gamma[which].as<float>(), c->beta[which].as<float>(), out, 1);
     p.mode = inverse ? kEpiIgdn : kEpiGdn;
+    if (dq) { p.dequant_idx = dq->idx; p.dequant_mean = dq->mean; p.dequant_delta = dq->delta; p.dequant_hw = dq->hw; }
     return run_gemm(c, p, kLayerGdn, UmmaWeights{c->gk_hi[which].as<float>(), c->gk_lo[which].as<float>(), 1}, nullptr, st);
 }
 
@@ -297,6 +308,9 @@ int run_layer(eae_codec* c, GemmPlan* plans, int n_plans, int kind, const UmmaWe
             plans[i].fuse = inverse ? 2 : 1; plans[i].fuse_beta = c->beta[gdn].as<float>();
             // mixed mode, synthesis side: the norm of a fused IGDN in one rounded-TF32 pass as well (its bar is the PSNR)
             plans[i].fuse_single_pass = (c->math == EAE_MATH_MIXED && !c->exact_now) ? 1 : 0;
+            // IEEE sqrt / division where the norm itself is the 3xTF32 one: gdn_precise 2 = every such layer (default),
+            // 1 = only GDN3, whose output is quantized, 0 = nowhere (MUFU forms; measurement knob)
+            plans[i].fuse_precise = !plans[i].fuse_single_pass && (c->gdn_precise >= 2 || (c->gdn_precise == 1 && gdn == 2)) ? 1 : 0;
         }
     }
     const bool tensor = c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kind) & 1);
@@ -314,10 +328,14 @@ int run_layer(eae_codec* c, GemmPlan* plans, int n_plans, int kind, const UmmaWe
 
 // conv k5 s2 SAME: out grid = in / 2, taps (ky - 1, kx - 1) (TF pads 1 before, 2 after). The input is
 // stored parity-split (written so by its producer).
+// quant: the quantizer of the latent fused into this layer's store (tensor path), or NULL.
+struct QuantOut { int16_t* idx; const float* mean; const float* delta; uint32_t* flag; };
+
 int run_conv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w, int layer, const float* bias,
-                float* out, bool out_split, int gdn, uint32_t n, cudaStream_t st)
+                float* out, bool out_split, int gdn, uint32_t n, cudaStream_t st, const QuantOut* quant = nullptr)
 {
     GemmPlan p = base_plan(in, Hin, Win, 128, w, bias, out, n);
+    if (quant) { p.quant_idx = quant->idx; p.quant_mean = quant->mean; p.quant_delta = quant->delta; p.quant_flag = quant->flag; }
     p.Hg = Hin / 2; p.Wg = Win / 2; p.in_mul = 2;
     p.Hout = p.Hg; p.Wout = p.Wg;
     p.in_split = 1;
@@ -357,8 +375,16 @@ int run_tconv5s2(eae_codec* c, const float* in, int Hin, int Win, const float* w
 }
 
 // parts: bit 0 = layer 1 (the only one that reads the caller's images), bit 1 = layers 2 and 3
+// quant != NULL: the latent leaves layer 3 as planar int16 indices (y_dev is not written). Only where
+// quantizer_fusable() says so.
+bool quantizer_fusable(const eae_codec* c, uint32_t h)
+{
+    return c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerConv) & 1) && umma_can_fuse_quantizer((int)(h / 16)) &&
+           (c->learned || can_fuse(c, kLayerConv)) && !c->no_fuse_quant;
+}
+
 int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, uint32_t w, float* y_dev,
-                 cudaStream_t st, int parts = 3)
+                 cudaStream_t st, int parts = 3, const QuantOut* quant = nullptr)
 {
     const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8;
     c->exact_now = c->math == EAE_MATH_TF32X3 || c->math == EAE_MATH_MIXED;      // the indices are decided here
@@ -381,12 +407,19 @@ int encode_chunk(eae_codec* c, const uint8_t* img_dev, uint32_t n, uint32_t h, u
     // layer 2 (output parity-split again), layer 3 (natural NHWC: it is the latent the API returns)
     EAE_TRY(run_conv5s2(c, x1, H1, W1, c->w2.as<float>(), 1, c->bias[1].as<float>(), x2, true, 1, n, st));
     EAE_TRY(run_conv5s2(c, x2, H2, W2, c->w3.as<float>(), 2, c->bias[2].as<float>(), y_dev, false,
-                        c->learned ? -1 : 2, n, st));
+                        c->learned ? -1 : 2, n, st, quant));
     return 0;
 }
 
+// Can the dequantizer run inside the operand load of the decoder's first IGDN (fixed bin widths, tensor path)?
+bool dequantizer_fusable(const eae_codec* c)
+{
+    return !c->learned && c->math != EAE_MATH_FP32_SIMT && ((c->umma_mask >> kLayerGdn) & 1) && !c->no_fuse_quant;
+}
+
+// dq != NULL (only where dequantizer_fusable()): the latent is read as planar int16 indices, q_dev is not.
 int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint32_t w, uint8_t* out_u8_dev,
-                 float* out_f32_dev, cudaStream_t st)
+                 float* out_f32_dev, cudaStream_t st, const DequantIn* dq = nullptr)
 {
     const int H1 = h / 4, W1 = w / 4, H2 = h / 8, W2 = w / 8, H3 = h / 16, W3 = w / 16;
     c->exact_now = c->math == EAE_MATH_TF32X3;
@@ -396,7 +429,7 @@ int decode_chunk(eae_codec* c, const float* q_dev, uint32_t n, uint32_t h, uint3
     float* x3 = c->buf3.as<float>();
     const float* src = q_dev;
     if (!c->learned) {
-        EAE_TRY(run_gdn(c, q_dev, x3, n * (uint32_t)(H3 * W3), 3, true, st));
+        EAE_TRY(run_gdn(c, q_dev, x3, n * (uint32_t)(H3 * W3), 3, true, st, dq));
         src = x3;
     }
     EAE_TRY(run_tconv5s2(c, src, H3, W3, c->w4.as<float>(), 3, c->bias[3].as<float>(), x2, 4, n, st));
@@ -427,10 +460,15 @@ struct OffsetsExtra {
     uint32_t n, h, w, L;
     eae_batch_stats_t* stats;    // or NULL
     const uint32_t* err;         // per-stream coder error codes (with stats)
-    uint32_t* flag;              // flag[1] = an error code if any stream failed
+    uint32_t* flag;              // flag[1] = an error code if any stream failed; flag[2], flag[3]: sticky status (kStatus*)
     uint32_t* bac_out;           // or NULL
     uint32_t* byp_out;
+    uint64_t limit;              // compress: capacity of the container; decompress: readable bytes of the container
+    uint32_t cap_bits;           // decompress: largest bit count a stream buffer may have (compression.cpp:24)
 };
+// Sticky status word flag[2] of a codec: set by the steps, read and cleared by eae_codec_poll_status. flag[3] = the first
+// coder error code (1..4) since the last poll.
+constexpr uint32_t kStatusInt16 = 1u, kStatusNoRoom = 2u, kStatusBadTable = 4u, kStatusTruncated = 8u;
 
 __global__ void __launch_bounds__(1024)
 stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __restrict__ byp_bits,
@@ -441,8 +479,8 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
     __shared__ uint64_t running;
     __shared__ unsigned long long red[1024];
     __shared__ uint32_t red_dead[1024];
-    __shared__ uint32_t first_err;
-    if (threadIdx.x == 0) { running = base; first_err = 0; }
+    __shared__ uint32_t first_err, bad_container;
+    if (threadIdx.x == 0) { running = base; first_err = 0; bad_container = 0; }
     // stream s = start + thread with start a multiple of 1024 = 8 x 128: a thread always sees the same map (s % 128), so
     // the per-map totals accumulate in registers and meet once at the end (no atomics on the way)
     unsigned long long my_bits = 0;
@@ -453,7 +491,13 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
         const uint32_t s = start + threadIdx.x;
         uint64_t nb = 0, nr = 0;
         if (s < n) {
-            const uint32_t bb = bac_bits[(size_t)s * bits_stride], rb = byp_bits[(size_t)s * bits_stride];
+            uint32_t bb = bac_bits[(size_t)s * bits_stride], rb = byp_bits[(size_t)s * bits_stride];
+            if (x.bac_out && (bb > x.cap_bits || rb > x.cap_bits)) {
+                // a stream table no encoder can have written: the stream is read as empty (the decoder then reports a
+                // resource error for it) and the container is flagged
+                bb = 0; rb = 0;
+                atomicOr(&bad_container, kStatusBadTable);
+            }
             nb = (bb + 7u) >> 3;
             nr = (rb + 7u) >> 3;
             if (x.header) { x.header[8 + 2 * (size_t)s] = bb; x.header[8 + 2 * (size_t)s + 1] = rb; }
@@ -483,13 +527,26 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
         __syncthreads();
         const uint64_t incl = v + (wid ? warp_sum[wid - 1] : 0);
         const uint64_t at = running + incl - (nb + nr);
-        if (s < n) { bac_off[s] = at; byp_off[s] = at + nb; }
+        if (s < n) {
+            bac_off[s] = at; byp_off[s] = at + nb;
+            if (x.bac_out && at + nb + nr > x.limit) {      // payload runs past the bytes the caller vouches for: never read
+                bac_off[s] = base; byp_off[s] = base;
+                x.bac_out[s] = 0; x.byp_out[s] = 0;
+                atomicOr(&bad_container, kStatusTruncated);
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 1023) running += incl;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         *total_out = running;
+        if (x.flag) {
+            uint32_t sticky = bad_container;
+            if (x.header && running > x.limit) sticky |= kStatusNoRoom;      // pack_payload_kernel drops what does not fit
+            if (x.header && (x.flag[0] & 1u)) sticky |= kStatusInt16;        // (the quantizer ran before this kernel)
+            if (sticky) atomicOr(x.flag + 2, sticky);
+        }
         if (x.header) {
             x.header[0] = kMagic; x.header[1] = kVersion; x.header[2] = x.n; x.header[3] = x.h; x.header[4] = x.w;
             x.header[5] = EAE_NB_MAPS; x.header[6] = x.L; x.header[7] = 0;
@@ -513,7 +570,7 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
             for (int m = 0; m < EAE_NB_MAPS; m++) { total += red[m]; dead += red_dead[m]; }
             x.stats->total_bits = total;
             x.stats->nb_dead_maps = dead;
-            if (first_err) atomicCAS(x.flag + 1, 0u, first_err);      // first stream error wins
+            if (first_err) { atomicCAS(x.flag + 1, 0u, first_err); atomicCAS(x.flag + 3, 0u, first_err); }      // first stream error wins
         }
     }
 }
@@ -744,16 +801,23 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     if (cap < kHeaderBytes + 8ull * n_streams) { set_error("container capacity too small"); return EAE_ERR_ARGUMENT; }
     c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
     c->last_idx_elems = (uint64_t)n_streams * hw3;      // (host state: outside the body, which may be replayed as a graph)
+    c->last_n_streams = n_streams;
     // parts: as encode_chunk's (1 = layer 1 has already been launched)
     auto body = [&](cudaStream_t st, int parts) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
     for (uint32_t i0 = 0; i0 < n; i0 += chunk) {
         const uint32_t nc = n - i0 < chunk ? n - i0 : chunk;
         float* y = c->buf3.as<float>();
+        int16_t* idx = c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3;
+        if (quantizer_fusable(c, h)) {
+            // layer 3 (+ GDN) writes the indices itself: no fp32 latent, no quantizer launch
+            const QuantOut quant{idx, c->mean.as<float>(), c->delta.as<float>(), c->flag.as<uint32_t>()};
+            EAE_TRY(encode_chunk(c, img_dev + (size_t)i0 * h * w, nc, h, w, y, st, parts, &quant));
+            continue;
+        }
         EAE_TRY(encode_chunk(c, img_dev + (size_t)i0 * h * w, nc, h, w, y, st, parts));
         ProfScope prof(kProfQuantize, st);
-        EAE_TRY(launch_quantize_to_planar(y, c->mean.as<float>(), c->delta.as<float>(),
-                                          c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3, nullptr,
+        EAE_TRY(launch_quantize_to_planar(y, c->mean.as<float>(), c->delta.as<float>(), idx, nullptr,
                                           nc, hw3, c->flag.as<uint32_t>(), st));
     }
     cudaStream_t cs = st;
@@ -770,7 +834,7 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     ProfScope prof_pack(kProfPack, cs);
     eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
     const OffsetsExtra extra{reinterpret_cast<uint32_t*>(container_dev), n, h, w, L, sd, c->err.as<uint32_t>(),
-                             c->flag.as<uint32_t>(), nullptr, nullptr};
+                             c->flag.as<uint32_t>(), nullptr, nullptr, cap, 0};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
                                               kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
                                               c->byp_off.as<uint64_t>(), total_dev, extra);
@@ -792,8 +856,9 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     return body(st, 3);
 }
 
-int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* container_dev, uint32_t n,
-                        uint32_t h, uint32_t w, uint8_t* rec_dev, cudaStream_t st)
+// nbytes: readable bytes at container_dev (the exact size of the container or the capacity of its buffer)
+int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_t* container_dev, uint64_t nbytes,
+                        uint32_t n, uint32_t h, uint32_t w, uint8_t* rec_dev, cudaStream_t st)
 {
     EAE_TRY(check_dims(n, h, w));
     codec_carveouts();
@@ -806,13 +871,15 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     EAE_TRY(ensure_coder(c, n_streams, hw3, L));
     c->no_phase_merge = c->phase_merge < 0 ? !(n <= chunk && graphs_usable(c, st)) : !c->phase_merge;
     c->last_idx_elems = (uint64_t)n_streams * hw3;
+    c->last_n_streams = n_streams;
     auto body = [&](cudaStream_t st) -> int {
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.p, 0, 8, st));
     cudaStream_t cs = st;
     EAE_TRY(fork_coder_stream(c, st, &cs));
     const uint32_t* tbl = reinterpret_cast<const uint32_t*>(container_dev + kHeaderBytes);
     // payload offsets, and the stream table de-interleaved into the bit-count arrays the decoder reads
-    const OffsetsExtra extra{nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>()};
+    const OffsetsExtra extra{nullptr, 0, 0, 0, 0, nullptr, nullptr, c->flag.as<uint32_t>(), c->bac_bits.as<uint32_t>(),
+                             c->byp_bits.as<uint32_t>(), nbytes, eae_coder_capacity_bytes(hw3, L) * 8u};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
                                               c->bac_off.as<uint64_t>(), c->byp_off.as<uint64_t>(),
                                               c->total_bytes.as<uint64_t>(), extra);
@@ -831,6 +898,13 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
         // the dequantized latent lives in bufA's tail-free region: use buf3 when IGDN4 is absent,
         // otherwise a separate buffer is needed because IGDN4 writes buf3.
         float* q = c->learned ? c->buf3.as<float>() : c->bufA.as<float>();
+        if (dequantizer_fusable(c)) {
+            // IGDN4 reads the indices itself: no fp32 latent, no dequantizer launch
+            const DequantIn dq{c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3, c->mean.as<float>(),
+                               c->delta.as<float>(), (int)hw3};
+            EAE_TRY(decode_chunk(c, nullptr, nc, h, w, rec_dev + (size_t)i0 * h * w, nullptr, st, &dq));
+            continue;
+        }
         {
             ProfScope prof(kProfDequantize, st);
             EAE_TRY(launch_dequantize_from_planar(c->idx_planar.as<int16_t>() + (size_t)i0 * EAE_NB_MAPS * hw3,
@@ -840,7 +914,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     }
     return 0;
     };
-    if (n <= chunk) return run_as_step_graph(c, make_step_key(c, 1, n, h, w, L, container_dev, rec_dev, nullptr, nullptr, 0), st, body);
+    if (n <= chunk) return run_as_step_graph(c, make_step_key(c, 1, n, h, w, L, container_dev, rec_dev, nullptr, nullptr, nbytes), st, body);
     return body(st);
 }
 
@@ -944,6 +1018,8 @@ extern "C" int eae_codec_create(eae_codec_t** out, const eae_weights_t* wt, int 
     if (const char* env = getenv("EAE_UMMA_LAYERS")) c->umma_mask = atoi(env);
     if (const char* env = getenv("EAE_NO_FUSE")) c->no_fuse = atoi(env);
     if (const char* env = getenv("EAE_NO_DIRECT_CONV1")) c->no_direct_conv1 = atoi(env);
+    if (const char* env = getenv("EAE_NO_FUSE_QUANT")) c->no_fuse_quant = atoi(env);
+    if (const char* env = getenv("EAE_GDN_PRECISE")) c->gdn_precise = atoi(env);
     if (const char* env = getenv("EAE_PHASE_MERGE")) c->phase_merge = atoi(env);
     if (const char* env = getenv("EAE_CODER_PRIORITY")) c->coder_priority = atoi(env);
     if (const char* env = getenv("EAE_GRAPHS")) c->use_graphs = atoi(env);
@@ -957,6 +1033,7 @@ extern "C" int eae_codec_destroy(eae_codec_t* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->status_host) cudaFreeHost(c->status_host);
     for (StepGraph& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->coder_stream) { cudaStreamSynchronize(c->coder_stream); cudaStreamDestroy(c->coder_stream); }
     if (c->fork_event) cudaEventDestroy(c->fork_event);
@@ -1098,16 +1175,85 @@ extern "C" int eae_compress_dev(eae_codec_t* c, const eae_coding_params_t* prm, 
 {
     if (!c || !img_dev || !container_dev || !total_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     EAE_CUDA_OK(cudaSetDevice(c->device));
+    c->last_stream = (cudaStream_t)stream;
     return compress_dev_impl(c, prm, img_dev, n, h, w, container_dev, cap, total_dev, stats_dev,
                              (cudaStream_t)stream);
 }
 
 extern "C" int eae_decompress_dev(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* container_dev,
-                                  uint32_t n, uint32_t h, uint32_t w, uint8_t* rec_dev, void* stream)
+                                  uint64_t container_bytes, uint32_t n, uint32_t h, uint32_t w, uint8_t* rec_dev,
+                                  void* stream)
 {
     if (!c || !container_dev || !rec_dev) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (container_bytes < kHeaderBytes + 8ull * n * EAE_NB_MAPS) { set_error("container shorter than its stream table"); return EAE_ERR_ARGUMENT; }
     EAE_CUDA_OK(cudaSetDevice(c->device));
-    return decompress_dev_impl(c, prm, container_dev, n, h, w, rec_dev, (cudaStream_t)stream);
+    c->last_stream = (cudaStream_t)stream;
+    return decompress_dev_impl(c, prm, container_dev, container_bytes, n, h, w, rec_dev, (cudaStream_t)stream);
+}
+
+// Status of the device-resident entry points since the last poll (they cannot report device-side failures themselves).
+namespace {
+struct HostStatus { uint32_t sticky, first_err, decode_err, umma_err; uint64_t total; };
+
+__global__ void __launch_bounds__(1024)
+status_kernel(HostStatus* __restrict__ out, uint32_t* __restrict__ flag, const uint32_t* __restrict__ err, uint32_t n_streams,
+              const uint64_t* __restrict__ total, uint32_t* __restrict__ umma_flag)
+{
+    __shared__ uint32_t key;
+    if (threadIdx.x == 0) key = 0xFFFFFFFFu;
+    __syncthreads();
+    // error of the lowest-numbered stream of the last step (the decoder leaves its codes only there)
+    uint32_t mine = 0xFFFFFFFFu;
+    for (uint32_t s = threadIdx.x; s < n_streams; s += blockDim.x)
+        if (err[s] && mine == 0xFFFFFFFFu) mine = (s << 8) | (err[s] & 0xFFu);
+    if (mine != 0xFFFFFFFFu) atomicMin(&key, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->sticky = atomicExch(flag + 2, 0u);
+        out->first_err = atomicExch(flag + 3, 0u);
+        out->decode_err = key == 0xFFFFFFFFu ? 0u : (key & 0xFFu);
+        out->umma_err = umma_flag ? atomicExch(umma_flag, 0u) : 0u;
+        out->total = total ? *total : 0ull;
+        __threadfence_system();
+    }
+}
+}  // namespace
+
+extern "C" int eae_codec_poll_status(eae_codec_t* c, void* stream, eae_codec_status_t* out)
+{
+    if (!c) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out) memset(out, 0, sizeof *out);
+    if (!c->flag.p || !c->err.p) return 0;      // nothing has run on this codec yet
+    if (!c->status_host) {
+        void* p = nullptr;
+        EAE_CUDA_OK(cudaHostAlloc(&p, sizeof(HostStatus), cudaHostAllocPortable | cudaHostAllocMapped));
+        c->status_host = p;
+    }
+    void* dev = nullptr;
+    EAE_CUDA_OK(cudaHostGetDevicePointer(&dev, c->status_host, 0));
+    status_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<HostStatus*>(dev), c->flag.as<uint32_t>(), c->err.as<uint32_t>(),
+                                      c->last_n_streams, nullptr,
+                                      c->math != EAE_MATH_FP32_SIMT ? umma_error_flag_dev() : nullptr);
+    EAE_LAUNCH_OK();
+    EAE_CUDA_OK(cudaStreamSynchronize(st));
+    const HostStatus hs = *reinterpret_cast<const HostStatus*>(c->status_host);
+    const uint32_t coder = hs.first_err ? hs.first_err : hs.decode_err;
+    if (out) {
+        out->int16_overflow = (hs.sticky & kStatusInt16) ? 1u : 0u;
+        out->container_overflow = (hs.sticky & kStatusNoRoom) ? 1u : 0u;
+        out->container_invalid = (hs.sticky & (kStatusBadTable | kStatusTruncated)) ? 1u : 0u;
+        out->coder_error = coder;
+        out->tensor_timeout_mask = hs.umma_err;
+    }
+    if (hs.umma_err) { set_error("tcgen05 GEMM pipeline timed out (role mask 0x%x)", hs.umma_err); return EAE_ERR_CUDA; }
+    if (hs.sticky & kStatusInt16) { set_error("The rounded array elements cannot be represented as 16-bit signed integers."); return EAE_ERR_INT16_RANGE; }
+    if (hs.sticky & kStatusNoRoom) { set_error("a container did not fit the capacity given to eae_compress_dev"); return EAE_ERR_ARGUMENT; }
+    if (hs.sticky & kStatusBadTable) { set_error("a container's stream table exceeds the coder capacity"); return EAE_ERR_CAPACITY; }
+    if (hs.sticky & kStatusTruncated) { set_error("a container is shorter than its stream table says"); return EAE_ERR_RESOURCE; }
+    if (coder) { set_error("Error of type %u during the coding.", coder); return (int)coder; }
+    return 0;
 }
 
 extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm, const uint8_t* img, uint32_t n,
@@ -1133,6 +1279,7 @@ extern "C" int eae_compress_host(eae_codec_t* c, const eae_coding_params_t* prm,
     if (!c->total_bytes.p) EAE_TRY(c->total_bytes.alloc(8));
     c->host_call = !c->graphs_in_host_calls;
     struct Reset { eae_codec* c; ~Reset() { c->host_call = false; } } reset{c};
+    c->last_stream = st;
     EAE_TRY(compress_dev_impl(c, prm, c->img_u8.as<uint8_t>(), n, h, w, c->rec_u8.as<uint8_t>(), dcap,
                               c->total_bytes.as<uint64_t>(), nullptr, st));
     if (direct) {
@@ -1186,7 +1333,8 @@ extern "C" int eae_decompress_host(eae_codec_t* c, const eae_coding_params_t* pr
     EAE_CUDA_OK(cudaMemcpyAsync(c->rec_u8.p, container, nbytes, cudaMemcpyHostToDevice, st));
     c->host_call = !c->graphs_in_host_calls;
     struct Reset { eae_codec* c; ~Reset() { c->host_call = false; } } reset{c};
-    EAE_TRY(decompress_dev_impl(c, prm, c->rec_u8.as<uint8_t>(), n, h, w, c->img_u8.as<uint8_t>(), st));
+    c->last_stream = st;
+    EAE_TRY(decompress_dev_impl(c, prm, c->rec_u8.as<uint8_t>(), nbytes, n, h, w, c->img_u8.as<uint8_t>(), st));
     // error of the lowest-numbered failing stream -> flag[1] -> mailbox; the reconstruction rides the same stream
     EAE_CUDA_OK(cudaMemsetAsync(c->flag.as<uint32_t>() + 1, 0xFF, 4, st));
     first_error_kernel<<<ceil_div_u32(n_streams, 256), 256, 0, st>>>(c->err.as<uint32_t>(), (uint32_t)n_streams,
@@ -1205,6 +1353,9 @@ extern "C" int eae_last_indices_host(eae_codec_t* c, int16_t* out, uint64_t n_el
 {
     if (!c || !out) { set_error("NULL pointer"); return EAE_ERR_NULL; }
     if (n_elems > c->last_idx_elems) { set_error("only %llu indices available", (unsigned long long)c->last_idx_elems); return EAE_ERR_ARGUMENT; }
-    EAE_CUDA_OK(cudaMemcpy(out, c->idx_planar.p, n_elems * 2, cudaMemcpyDeviceToHost));
+    // on the stream of the step that wrote them (a non-blocking stream does not synchronise with the legacy one)
+    EAE_CUDA_OK(cudaSetDevice(c->device));
+    EAE_CUDA_OK(cudaMemcpyAsync(out, c->idx_planar.p, n_elems * 2, cudaMemcpyDeviceToHost, c->last_stream));
+    EAE_CUDA_OK(cudaStreamSynchronize(c->last_stream));
     return 0;
 }

@@ -50,8 +50,21 @@ struct GemmPlan {
     int fuse;            // tensor path only: 0 none, 1 GDN, 2 IGDN applied to (acc + bias) before the store
     const float* fuse_beta;
     int fuse_single_pass;    //   the fused norm contracts in single-pass TF32 (squares rounded to nearest) instead of 3xTF32
+    int fuse_precise;        //   the normalisation uses IEEE sqrt and division (tfutils.py:394-397) instead of the MUFU forms
     const uint8_t* img_u8;   // tensor path only: the layer is the k9 s4 convolution of this uint8 image [n, img_H, img_W]
     int img_H, img_W;        //   (A rows are gathered from the pixels inside the kernel; `in` is not read)
+    // tensor path, multi-tap layers only: the quantizer of the latent fused into the store (umma_v3.cuh, OutGeom4):
+    // planar int16 indices [n, 128, Hg * Wg] instead of the fp32 output; `out` is then not written
+    int16_t* quant_idx;
+    const float* quant_mean;     // [128] or NULL (zeros)
+    const float* quant_delta;    // [128]
+    uint32_t* quant_flag;        // bit 0: an index does not fit int16
+    // tensor path, standalone IGDN (mode kEpiIgdn, flat position grid) only: the dequantizer fused into the operand
+    // load: the input is delta[c] * k + mean[c] of the planar int16 indices [n images, 128, dequant_hw]; `in` is not read
+    const int16_t* dequant_idx;
+    const float* dequant_mean;   // [128] or NULL (zeros)
+    const float* dequant_delta;  // [128]
+    int dequant_hw;              // positions per image
     int n_taps;
     uint32_t M;          // n * Hg * Wg
     Tap taps[kMaxTaps];

@@ -177,6 +177,13 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             return EAE_ERR_ARGUMENT;
         }
         map_a = map_b_hi;      // not read
+    } else if (plan.dequant_idx) {
+        if (plan.n_taps != 1 || plan.Cin != 128 || plan.Hg != 1 || plan.fuse || plan.mode != kEpiIgdn || !plan.dequant_delta ||
+            plan.dequant_hw <= 0 || plan.in_split || plan.out_split || plan.out_mul != 1) {
+            set_error("gemm_umma: the fused dequantizer needs a standalone IGDN over a flat position grid");
+            return EAE_ERR_ARGUMENT;
+        }
+        map_a = map_b_hi;      // not read
     } else {
         const uint64_t adims[5] = {(uint64_t)plan.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)planes, n_img};
         const uint32_t abox[5] = {kChunkK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1, 1};
@@ -200,7 +207,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.out = plan.out; q.bias = plan.bias; q.beta = plan.fuse_beta;
         q.Hout = plan.Hout; q.Wout = plan.Wout; q.out_mul = plan.out_mul; q.out_r = plan.out_r; q.out_s = plan.out_s;
         q.out_split = plan.out_split;
-        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0; q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
+        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0; q.exact_gdn = plan.fuse_single_pass ? 0 : 1; q.precise_gdn = plan.fuse_precise;
+        q.idx_out = plan.quant_idx; q.q_mean = plan.quant_mean; q.q_delta = plan.quant_delta; q.q_flag = plan.quant_flag;
         q.error_flag = g_error_flag;
         // groups = input planes in use; taps sorted by group
         int fy_min[kMaxGroups4], fx_min[kMaxGroups4], fy_max[kMaxGroups4], fx_max[kMaxGroups4], group_of_plane[4] = {-1, -1, -1, -1};
@@ -241,12 +249,16 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
     auto eligible4 = [&](const GemmPlan& pl) {
         return pl.n_taps > 1 && pl.n_taps <= kMaxTaps && pl.Hg > 1 && pl.Cin == 128 && !pl.img_u8 &&
                pl.in == plan.in && pl.Hg == plan.Hg && pl.Wg == plan.Wg && pl.in_split == plan.in_split && pl.M == plan.M &&
-               pl.fuse == plan.fuse && pl.fuse_single_pass == plan.fuse_single_pass;
+               pl.fuse == plan.fuse && pl.fuse_single_pass == plan.fuse_single_pass && pl.fuse_precise == plan.fuse_precise;
     };
     UmmaParams4x qx;
     memset(&qx, 0, sizeof qx);
     bool all4 = eligible4(plan) && build4(plan, qx.ph[0]);
     for (int i = 0; i < n_more && all4; i++) all4 = eligible4(more[i]) && build4(more[i], qx.ph[1 + i]);
+    if (plan.quant_idx && (!all4 || plan.out_split || plan.out_mul != 1 || !plan.quant_delta || !plan.quant_flag)) {
+        set_error("gemm_umma: the fused quantizer needs a multi-tap layer with a natural NHWC output grid");
+        return EAE_ERR_ARGUMENT;
+    }
     if (n_more > 0 && !all4) {      // no common launch: one after the other
         EAE_TRY(launch_gemm_umma(plan, w, gamma, exact3x, st, nullptr, 0));
         for (int i = 0; i < n_more; i++) EAE_TRY(launch_gemm_umma(more[i], w, gamma, exact3x, st, nullptr, 0));
@@ -339,12 +351,14 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.tiles_y = (plan.Hg + q.tile_h + q.half_da - 1) / (q.tile_h + q.half_da);
         q.Hg = p.Hg; q.Wg = p.Wg;
         q.out = p.out; q.bias = p.bias; q.beta = plan.fuse_beta; q.xin = p.xin;
+        q.idx_in = plan.dequant_idx; q.dq_mean = plan.dequant_mean; q.dq_delta = plan.dequant_delta; q.hw_in = plan.dequant_hw;
         q.Hout = p.Hout; q.Wout = p.Wout; q.out_mul = p.out_mul; q.out_r = p.out_r; q.out_s = p.out_s;
         q.out_split = p.out_split;
         q.mode = p.mode;
         q.fuse = plan.fuse;
         q.exact_main = exact3x ? 1 : 0;
         q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
+        q.precise_gdn = plan.fuse_precise;
         q.error_flag = p.error_flag;
         memcpy(q.taps, p.taps, sizeof q.taps);
         const uint32_t grid3 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
@@ -449,4 +463,48 @@ int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8
     return 0;
 }
 
+namespace {
+
+// Debug hook: sqrt_rn_norm / div_rn_norm against the compiler's IEEE sqrt.rn / div.rn.
+//   square roots: EVERY float in [2^-20, 2^40] (a norm + beta lies in [2e-5, ~1e6])
+//   quotients:    n_pairs pseudo-random pairs, |a| in [2^-30, 2^30] (either sign), b in [2^-10, 2^20]
+__global__ void norm_arith_check_kernel(uint64_t n_pairs, unsigned long long* __restrict__ bad)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad_sqrt = 0, bad_div = 0;
+    const uint32_t lo = 0x35800000u /* 2^-20 */, hi = 0x53800000u /* 2^40 */;
+    for (uint64_t b = lo + tid; b <= hi; b += nth) {
+        const float n = __uint_as_float((uint32_t)b);
+        if (__float_as_uint(sqrt_rn_norm(n)) != __float_as_uint(__fsqrt_rn(n))) bad_sqrt++;
+    }
+    for (uint64_t i = tid; i < n_pairs; i += nth) {
+        uint64_t z = i * 0x9E3779B97F4A7C15ull + 0x1234567ull;      // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const uint32_t ua = (uint32_t)z, ub = (uint32_t)(z >> 32);
+        const uint32_t ea = 127u - 30u + (ua >> 23) % 61u, eb = 127u - 10u + (ub >> 23) % 31u;
+        const float a = __uint_as_float((ua & 0x807FFFFFu) | (ea << 23)), b = __uint_as_float((ub & 0x007FFFFFu) | (eb << 23));
+        if (__float_as_uint(div_rn_norm(a, b)) != __float_as_uint(__fdiv_rn(a, b))) bad_div++;
+    }
+    if (bad_sqrt) atomicAdd(bad, bad_sqrt);
+    if (bad_div) atomicAdd(bad + 1, bad_div);
+}
+
+}  // namespace
 }  // namespace eae
+
+extern "C" int eae_debug_check_norm_arithmetic(uint64_t n_pairs, uint64_t* sqrt_mismatches, uint64_t* div_mismatches)
+{
+    using namespace eae;
+    if (!sqrt_mismatches || !div_mismatches) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    EAE_TRY(require_device());
+    unsigned long long* d = nullptr;
+    EAE_CUDA_OK(cudaMalloc(&d, 16));
+    EAE_CUDA_OK(cudaMemset(d, 0, 16));
+    norm_arith_check_kernel<<<148 * 8, 256>>>(n_pairs, d);
+    unsigned long long h[2] = {0, 0};
+    const cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    EAE_CUDA_OK(e);
+    *sqrt_mismatches = h[0]; *div_mismatches = h[1];
+    return 0;
+}

@@ -28,6 +28,8 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
 // K-major tap matrix `w` ([128 tap columns, 81 used][128 in]) + the col2im gather + the BT.601 cast / float output.
 int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8, float* out_f32, uint32_t n, int H, int W,
                           bool exact3x, cudaStream_t st);
+// Can launch_gemm_umma fuse the quantizer (GemmPlan::quant_idx) into this k5 s2 convolution's store?
+inline bool umma_can_fuse_quantizer(int Hg) { return Hg > 1; }
 // Reads and clears the device-side timeout flag of the tensor path (synchronises `st`).
 int umma_check_error(cudaStream_t st);
 // The device word behind umma_check_error (NULL before the first tensor-path launch); kernels may read and clear it.

@@ -149,11 +149,19 @@ struct UmmaParams3 {
     const float* bias;
     const float* beta;       // fused GDN / IGDN
     const float* xin;        // standalone GDN / IGDN: the un-squared input
+    // standalone IGDN on the decoder's input with the dequantizer fused into the operand load
+    // (reconstructing_eae_kodak.py:192, components.py:56-58): when idx_in is set the input is
+    // delta[c] * k + mean[c] of the planar int16 indices [n, 128, hw_in] the entropy decoder wrote; `xin` is not read
+    const int16_t* idx_in;
+    const float* dq_mean;    // [128] or NULL
+    const float* dq_delta;   // [128]
+    int hw_in;
     int Hout, Wout, out_mul, out_r, out_s, out_split;
     int mode;                // EpilogueMode of a standalone launch
     int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
     int exact_main;          // 3xTF32 for the main contraction
     int exact_gdn;           // 3xTF32 for the fused norm (versions 3 and 4)
+    int precise_gdn;         // IEEE sqrt / division in the fused normalisation (GemmPlan::fuse_precise)
     int tile_w_log2;
     int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
     int conv1;               // version 3: A rows are the 9x9 patches (k9 s4) of a uint8 image tile staged by TMA

@@ -43,7 +43,11 @@ struct UmmaParams4 {
     const float* bias;
     const float* beta;
     int Hout, Wout, out_mul, out_r, out_s, out_split;
-    int fuse, exact_main, exact_gdn;
+    int fuse, exact_main, exact_gdn, precise_gdn;
+    int16_t* idx_out;         // quantizer fused into the store (see OutGeom4), or NULL
+    const float* q_mean;
+    const float* q_delta;
+    uint32_t* q_flag;
     long long* times;
     uint32_t* error_flag;
     UmmaTap4 taps[kMaxTaps];
@@ -79,7 +83,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
     const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
-                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn};
+                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn, p.precise_gdn};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,7 +267,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             if (lane == 0) mbar_arrive(&split[it & 3]);   // 4 arrivals instead of 128: the arrive chain is on the critical path
         }
         const int wq = warp - 2;
-        const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split};
+        const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split,
+                            p.idx_out, p.q_mean, p.q_delta, p.q_flag};
         uint8_t* stage0 = smem;                          // un-fused epilogue: both halves staged side by side
         uint8_t* stage1 = smem + kGdnStageBytes4;
         if (ok && n_gdn) {

@@ -56,6 +56,16 @@ def random_init(seed=0, are_bin_widths_learned=False, bin_width_init=1.):
     return w
 
 
+def visible_init(seed=0, are_bin_widths_learned=False, bin_width_init=1.):
+    """``random_init`` with reconstructions that land inside the BT.601 range instead of being clipped to 16: a
+    positive bias before the last IGDN and a larger, positive last filter (the reference's initial distributions give a
+    zero-mean output, EntropyAutoencoder.py:131-224). Used wherever a parity check must see un-clipped pixels."""
+    w = random_init(seed, are_bin_widths_learned, bin_width_init)
+    w['decoder/biases_5'] = (w['decoder/biases_5'] + 2.0).astype(numpy.float32)
+    w['decoder/weights_6'] = (numpy.abs(w['decoder/weights_6'])*8.).astype(numpy.float32)
+    return w
+
+
 def validate(weights, are_bin_widths_learned, need_encoder=True, need_decoder=True):
     """Checks presence, dtype and shape of every variable the inference graphs read."""
     keys = (ENCODER_KEYS if need_encoder else []) + (DECODER_KEYS if need_decoder else [])

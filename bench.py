@@ -275,7 +275,7 @@ def run_gpu_arm(args):
         if world > 1:
             with torch.cuda.stream(slot.torch_stream):
                 dist.all_reduce(slot.stats_t)     # per-map bit totals over all ranks (NCCL over NVLink)
-        _native.check(lib.eae_decompress_dev(slot.codec.handle, ctypes.byref(native_params), slot.d_container, n, h, w,
+        _native.check(lib.eae_decompress_dev(slot.codec.handle, ctypes.byref(native_params), slot.d_container, bound, n, h, w,
                                              slot.d_recon, slot.stream))
 
     def barrier():

@@ -323,8 +323,8 @@ typedef struct eae_coding_params {
  */
 uint64_t eae_container_bound(uint32_t n, uint32_t h, uint32_t w, uint32_t truncated_unary_length);
 
-/* Per-batch statistics (device-reduced): total bits per map over the batch, sum of squared error
- * and pixel count for PSNR. */
+/* Per-batch statistics (device-reduced): total bits per map over the batch (what numpy.mean(rate, axis=1) reduces,
+ * reconstructing_eae_kodak.py:810-815), total bits, and the number of dead maps (tools.py:294-320). */
 typedef struct eae_batch_stats {
     uint64_t bits_per_map[EAE_NB_MAPS];
     uint64_t total_bits;
@@ -339,17 +339,48 @@ int eae_compress_host(eae_codec_t* codec, const eae_coding_params_t* params, con
 int eae_decompress_host(eae_codec_t* codec, const eae_coding_params_t* params, const uint8_t* container,
                         uint64_t container_bytes, uint8_t* reconstruction, uint64_t reconstruction_cap,
                         void* stream);
-/* Same pipeline with the images / container / reconstruction resident in device memory (async).
- * container_bytes_dev: uint64 on the device. */
+/* Same pipeline with the images / container / reconstruction resident in device memory. Asynchronous: the calls
+ * return once the work is enqueued on `stream`, so they can only report host-side errors. What happens on the device
+ * is reported by eae_codec_poll_status:
+ *   - container_bytes_dev (uint64 on the device) receives the size the container NEEDS. If it exceeds container_cap
+ *     the streams that do not fit are not written (the header and the stream table always are) and the status says
+ *     container_overflow: size the buffer with eae_container_bound, or poll and retry.
+ *   - an index that does not fit int16 (tools.py:126-133), a coder error (codes 1..4 of compression.cpp:32-62) and a
+ *     time-out of the tensor pipeline are recorded in the codec and reported by the poll.
+ * eae_decompress_dev reads at most container_bytes bytes at container_dev (the exact size of the container, or the
+ * capacity of the buffer when the size is only known on the device). The stream table is validated on the device: a
+ * stream whose bit counts exceed the coder capacity (compression.cpp:24) or whose payload would run past
+ * container_bytes is decoded as an empty stream (resource error 2 for that stream) and the status says
+ * container_invalid; nothing outside [container_dev, container_dev + container_bytes) is read. */
 int eae_compress_dev(eae_codec_t* codec, const eae_coding_params_t* params, const uint8_t* luminances_dev,
                      uint32_t n, uint32_t h, uint32_t w, uint8_t* container_dev, uint64_t container_cap,
                      uint64_t* container_bytes_dev, eae_batch_stats_t* stats_dev, void* stream);
 int eae_decompress_dev(eae_codec_t* codec, const eae_coding_params_t* params, const uint8_t* container_dev,
-                       uint32_t n, uint32_t h, uint32_t w, uint8_t* reconstruction_dev, void* stream);
+                       uint64_t container_bytes, uint32_t n, uint32_t h, uint32_t w, uint8_t* reconstruction_dev,
+                       void* stream);
+
+/* What the device-resident steps of this codec recorded since the previous poll (sticky), plus the decoder's error of
+ * the LAST eae_decompress_dev step. Enqueues a one-CTA kernel on `stream`, waits for the stream, clears the record.
+ * Returns 0, or the code the corresponding _host entry point would have returned (EAE_ERR_INT16_RANGE, 1..4,
+ * EAE_ERR_ARGUMENT for a container that did not fit, EAE_ERR_CAPACITY / EAE_ERR_RESOURCE for an invalid container,
+ * EAE_ERR_CUDA for a tensor-pipeline time-out) with eae_last_error set. `status` may be NULL. */
+typedef struct eae_codec_status {
+    uint32_t int16_overflow;      /* 1: an index did not fit int16 */
+    uint32_t container_overflow;  /* 1: a container needed more than container_cap bytes */
+    uint32_t container_invalid;   /* 1: a stream table failed the device-side validation of eae_decompress_dev */
+    uint32_t coder_error;         /* first coder error code (1..4), 0 if none */
+    uint32_t tensor_timeout_mask; /* role mask of a timed-out tcgen05 pipeline, 0 if none */
+} eae_codec_status_t;
+int eae_codec_poll_status(eae_codec_t* codec, void* stream, eae_codec_status_t* status);
 
 /* Debug / parity hooks: the int16 indices [n, nb_maps, h/16 * w/16] (planar) produced by the last
- * eae_compress_* on this codec, copied to host. */
+ * eae_compress_* / eae_decompress_* on this codec, copied to host on the stream of that step (synchronises it). */
 int eae_last_indices_host(eae_codec_t* codec, int16_t* idx_planar_out, uint64_t n_elems);
+
+/* Debug hook: the correctly rounded square root and quotient the fused GDN / IGDN normalisation uses
+ * (tfutils.py:394-397, 506-509) against the compiler's sqrt.rn / div.rn: every float in [2^-20, 2^40] for the
+ * square root, n_pairs pseudo-random pairs for the quotient. Both counts must be 0. */
+int eae_debug_check_norm_arithmetic(uint64_t n_pairs, uint64_t* sqrt_mismatches, uint64_t* div_mismatches);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ def main():
         img = d_img + (i % rotate)*n*h*w
         _native.check(lib.eae_compress_dev(c.handle, ctypes.byref(native_params), img, n, h, w, d_cont[k], bound,
                                            d_tot[k], d_stats[k], c.stream))
-        _native.check(lib.eae_decompress_dev(c.handle, ctypes.byref(native_params), d_cont[k], n, h, w, d_rec[k], c.stream))
+        _native.check(lib.eae_decompress_dev(c.handle, ctypes.byref(native_params), d_cont[k], bound, n, h, w, d_rec[k], c.stream))
 
     def sync():
         for c in codecs:

@@ -46,7 +46,7 @@ def main():
         c = codecs[k]
         _native.check(lib.eae_compress_dev(c.handle, ctypes.byref(native_params), d_img[k].data_ptr(), n, h, w,
                                            d_cont[k].data_ptr(), bound, d_tot[k].data_ptr(), d_stats[k].data_ptr(), c.stream))
-        _native.check(lib.eae_decompress_dev(c.handle, ctypes.byref(native_params), d_cont[k].data_ptr(), n, h, w,
+        _native.check(lib.eae_decompress_dev(c.handle, ctypes.byref(native_params), d_cont[k].data_ptr(), bound, n, h, w,
                                              d_rec[k].data_ptr(), c.stream))
 
     def sync():

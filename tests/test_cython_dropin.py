@@ -75,5 +75,14 @@ def test_reference_known_answers_through_the_unmodified_binding(native, golden):
     assert bits_a == bits_b and numpy.array_equal(rec_a, flat) and numpy.array_equal(rec_b, flat)
     with pytest.raises(RuntimeError, match='Error of type 4'):                         # test_lossless.py:329-375
         module.compress_lossless_flattened_map(numpy.array([3, 1], dtype=numpy.int16), numpy.array([.5, 1.5, .5]))
-    with pytest.raises(OverflowError):                                                 # interface_cython.pyx:50-52
-        module.compress_lossless_flattened_map(numpy.array([3, 1], dtype=numpy.int16), 0.5*numpy.ones(300))
+    # interface_cython.pyx:50-52 assigns `probabilities.size` to a uint8. Its comment expects Cython to raise; Cython 3
+    # reads the size of a typed buffer in C and the assignment wraps (300 -> 44), for the reference's own build as for this
+    # one. Either behaviour is the binding's, not the library's: the library must see L <= 255 and answer accordingly.
+    two = numpy.array([3, 1], dtype=numpy.int16)
+    try:
+        (rec_w, bits_w) = module.compress_lossless_flattened_map(two, 0.5*numpy.ones(300))
+    except OverflowError:
+        pass
+    else:
+        (rec_44, bits_44) = module.compress_lossless_flattened_map(two, 0.5*numpy.ones(300 & 0xFF))
+        assert bits_w == bits_44 and numpy.array_equal(rec_w, rec_44) and numpy.array_equal(rec_w, two)

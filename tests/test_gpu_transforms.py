@@ -21,6 +21,10 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 PARITY_MODES = ['fp32', 'tf32x3']
+# Largest distance (in bin widths) a mismatching coefficient may have to its bin edge. north_star states 1e-5: the CUDA-core
+# fp32 path is held to it. The 3xTF32 tensor path accumulates ~1 200 partial products per output in a TMEM accumulator that
+# truncates: its measured worst is printed by the tests and bounded here.
+EDGE_BOUND = {'fp32': 1e-5, 'tf32x3': 1e-4}
 
 
 def index_agreement(y_gpu, y_ref64, delta=1.0):
@@ -34,14 +38,7 @@ def index_agreement(y_gpu, y_ref64, delta=1.0):
     return (frac, worst, int(diff.sum()))
 
 
-def visible_weights(seed, learned):
-    """Random-init weights whose reconstructions land inside the BT.601 range instead of being clipped
-    to 16: a positive bias before the last IGDN and a larger last filter (the reference's initial
-    distributions give a zero-mean output, see EntropyAutoencoder.py:131-224)."""
-    w = wts.random_init(seed, learned)
-    w['decoder/biases_5'] = (w['decoder/biases_5'] + 2.0).astype(numpy.float32)
-    w['decoder/weights_6'] = (numpy.abs(w['decoder/weights_6'])*8.).astype(numpy.float32)
-    return w
+visible_weights = wts.visible_init
 
 
 @pytest.mark.parametrize('math', PARITY_MODES)
@@ -61,7 +58,8 @@ def test_encoder_decoder_small(native, learned, math):
     scale = numpy.abs(y64).max()
     assert numpy.abs(y - y64).max() <= 5e-5*scale, numpy.abs(y - y64).max()/scale
     (frac, worst, nb) = index_agreement(y, y64)
-    assert frac >= 0.9999 and worst < 1e-4, (frac, worst, nb)
+    print('index clause ({}, learned={}): {} mismatches of {}, worst edge distance {:.2e}'.format(math, learned, nb, y.size, worst))
+    assert frac >= 0.9999 and worst < EDGE_BOUND[math], (frac, worst, nb)
     # decoder on the oracle's quantized latent: float output, then the uint8 cast
     q = oracle_glue.quantize_per_map(y32, numpy.ones(128, dtype=numpy.float32))
     dec = IsolatedDecoder(4, h, wd, learned)
@@ -100,7 +98,8 @@ def test_kodak_size_image_against_oracle(native, math):
     y32 = T.encoder(lum.astype(numpy.float32), w, False)
     (frac, worst, nb) = index_agreement(y, y64)
     (frac32, _, nb32) = index_agreement(y32, y64)
-    assert frac >= 0.9999 and worst < 1e-4, (frac, worst, nb, frac32, nb32)
+    print('index clause ({}): {} mismatches of {}, worst edge distance {:.2e}; fp32 oracle vs fp64: {}'.format(math, nb, y.size, worst, nb32))
+    assert frac >= 0.9999 and worst < EDGE_BOUND[math], (frac, worst, nb, frac32, nb32)
     q = oracle_glue.quantize_per_map(y32, numpy.ones(128, dtype=numpy.float32))
     rec = codec.decode(q)[..., 0]
     want = oracle_glue.cast_bt601(T.decoder(q, w, False))[..., 0]
@@ -203,3 +202,40 @@ def test_random_shapes_against_the_oracle(native):
         assert numpy.abs(rec_f - want_f).max() < 1e-3*max(1., numpy.abs(want_f).max()), (h, wd, learned)
         diff = numpy.abs(codec.decode(q).astype(numpy.int32) - oracle_glue.cast_bt601(want_f).astype(numpy.int32))
         assert diff.max() <= 1 and (diff != 0).mean() < 2e-2, (h, wd, learned, diff.max(), (diff != 0).mean())
+
+
+def test_fused_normalisation_uses_correctly_rounded_sqrt_and_division(native):
+    """tfutils.py:394-397, 506-509 divide by / multiply with sqrt(norm + beta). The fused GDN / IGDN epilogues use inlined
+    fast paths of the IEEE sequences (csrc/umma_v3.cuh, sqrt_rn_norm / div_rn_norm); they must be bit-equal to sqrt.rn /
+    div.rn for every float a norm can be (exhaustive over [2^-20, 2^40]) and on 2^32 pseudo-random quotients."""
+    import ctypes
+    (bad_sqrt, bad_div) = (ctypes.c_uint64(1), ctypes.c_uint64(1))
+    native.check(native.lib().eae_debug_check_norm_arithmetic(1 << 32, ctypes.byref(bad_sqrt), ctypes.byref(bad_div)))
+    assert (bad_sqrt.value, bad_div.value) == (0, 0)
+
+
+def test_fused_quantizer_and_dequantizer_equal_the_separate_launches(native, golden, monkeypatch):
+    """The quantizer in the store of the last analysis layer (planar int16 straight from the GDN3 epilogue) and the
+    dequantizer in the operand load of IGDN4 against the separate quantize / dequantize launches (EAE_NO_FUSE_QUANT=1):
+    same container byte for byte, same reconstruction, for both arithmetic modes of the tensor path and for latent grids
+    that are not multiples of a tile."""
+    rng = numpy.random.default_rng(14)
+    w = visible_weights(5, False)
+    mean = (0.05*golden.map_mean('1_10000')).astype(numpy.float32)
+    for (n, h, wd) in ((3, 128, 192), (1, 48, 80), (2, 16, 272), (1, 400, 16)):
+        lum = util.synthetic_luma(rng, n, h, wd)
+        for (math, delta) in (('mixed', 1.), ('tf32x3', 0.5)):
+            params = native_codec.CodingParams(delta*numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'), mean)
+            monkeypatch.delenv('EAE_NO_FUSE_QUANT', raising=False)
+            fused = native_codec.Codec(w, False, math=math)
+            blob = numpy.array(fused.compress(lum, params), copy=True)
+            rec = numpy.array(fused.decompress(blob, params), copy=True)
+            monkeypatch.setenv('EAE_NO_FUSE_QUANT', '1')
+            plain = native_codec.Codec(w, False, math=math)
+            assert numpy.array_equal(plain.compress(lum, params), blob), (n, h, wd, math)
+            assert numpy.array_equal(plain.decompress(blob, params), rec), (n, h, wd, math)
+            # and the indices are those of the latent the API returns
+            y = plain.encode(lum[..., None])
+            k = numpy.rint((y - mean.reshape((1, 1, 1, -1)))/numpy.float32(delta)).astype(numpy.int16)
+            assert numpy.array_equal(fused.last_indices(n, h, wd), k.reshape(n, -1, 128).transpose(0, 2, 1))
+    monkeypatch.delenv('EAE_NO_FUSE_QUANT', raising=False)
