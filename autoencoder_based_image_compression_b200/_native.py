@@ -97,6 +97,8 @@ PROTOTYPES = {
                                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     'eae_histogram_maps_host': (c_int, [c_void_p, u32, u32, u32, u32, c_int, c_void_p, c_void_p, c_void_p,
                                         u32, P(u32), c_void_p, c_void_p]),
+    'eae_histogram_streams_dev': (c_int, [c_void_p, u32, u32, u32, c_int, c_void_p, c_void_p, c_void_p, c_void_p, u32,
+                                            c_void_p]),
     'eae_coder_slot_bytes': (u32, [u32, u32]),
     'eae_nhwc_to_planar_i16_dev': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p]),
     'eae_planar_to_nhwc_i16_dev': (c_int, [c_void_p, c_void_p, u32, u32, u32, c_void_p]),
@@ -128,6 +130,7 @@ PROTOTYPES = {
     'eae_compress_dev': (c_int, [c_void_p, P(CodingParams), c_void_p, u32, u32, u32, c_void_p, u64, c_void_p,
                                  c_void_p, c_void_p]),
     'eae_decompress_dev': (c_int, [c_void_p, P(CodingParams), c_void_p, u64, u32, u32, u32, c_void_p, c_void_p]),
+    'eae_codec_set_stats_accumulator': (c_int, [c_void_p, c_void_p]),
     'eae_codec_poll_status': (c_int, [c_void_p, c_void_p, P(CodecStatus)]),
     'eae_debug_check_norm_arithmetic': (c_int, [u64, P(u64), P(u64)]),
     'eae_last_indices_host': (c_int, [c_void_p, c_void_p, u64]),

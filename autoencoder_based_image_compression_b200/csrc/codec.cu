@@ -93,6 +93,7 @@ struct eae_codec {
     void* status_host = nullptr;          // pinned HostStatus of eae_codec_poll_status
     cudaStream_t last_stream = nullptr;   // stream of the last compress / decompress step
     uint32_t last_n_streams = 0;
+    eae_batch_stats_t* stats_acc = nullptr;   // device accumulator of the per-step statistics (caller-owned), or NULL
 };
 
 struct HostMailbox {
@@ -463,6 +464,7 @@ struct OffsetsExtra {
     uint32_t* flag;              // flag[1] = an error code if any stream failed; flag[2], flag[3]: sticky status (kStatus*)
     uint32_t* bac_out;           // or NULL
     uint32_t* byp_out;
+    eae_batch_stats_t* acc;      // compress: running totals over steps (atomic adds), or NULL
     uint64_t limit;              // compress: capacity of the container; decompress: readable bytes of the container
     uint32_t cap_bits;           // decompress: largest bit count a stream buffer may have (compression.cpp:24)
 };
@@ -561,6 +563,7 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
             uint32_t dead = 0;
             for (int k = 0; k < 1024 / EAE_NB_MAPS; k++) { bits += red[threadIdx.x + k * EAE_NB_MAPS]; dead += red_dead[threadIdx.x + k * EAE_NB_MAPS]; }
             x.stats->bits_per_map[threadIdx.x] = bits;
+            if (x.acc) atomicAdd(reinterpret_cast<unsigned long long*>(&x.acc->bits_per_map[threadIdx.x]), bits);
             red[threadIdx.x] = bits;
             red_dead[threadIdx.x] = dead;
         }
@@ -570,6 +573,10 @@ stream_offsets_kernel(const uint32_t* __restrict__ bac_bits, const uint32_t* __r
             for (int m = 0; m < EAE_NB_MAPS; m++) { total += red[m]; dead += red_dead[m]; }
             x.stats->total_bits = total;
             x.stats->nb_dead_maps = dead;
+            if (x.acc) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&x.acc->total_bits), total);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&x.acc->nb_dead_maps), dead);
+            }
             if (first_err) { atomicCAS(x.flag + 1, 0u, first_err); atomicCAS(x.flag + 3, 0u, first_err); }      // first stream error wins
         }
     }
@@ -834,7 +841,7 @@ int compress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint8_
     ProfScope prof_pack(kProfPack, cs);
     eae_batch_stats_t* sd = stats_dev ? stats_dev : c->stats.as<eae_batch_stats_t>();
     const OffsetsExtra extra{reinterpret_cast<uint32_t*>(container_dev), n, h, w, L, sd, c->err.as<uint32_t>(),
-                             c->flag.as<uint32_t>(), nullptr, nullptr, cap, 0};
+                             c->flag.as<uint32_t>(), nullptr, nullptr, c->stats_acc, cap, 0};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(c->bac_bits.as<uint32_t>(), c->byp_bits.as<uint32_t>(), 1, n_streams,
                                               kHeaderBytes + 8ull * n_streams, c->bac_off.as<uint64_t>(),
                                               c->byp_off.as<uint64_t>(), total_dev, extra);
@@ -879,7 +886,7 @@ int decompress_dev_impl(eae_codec* c, const eae_coding_params_t* prm, const uint
     const uint32_t* tbl = reinterpret_cast<const uint32_t*>(container_dev + kHeaderBytes);
     // payload offsets, and the stream table de-interleaved into the bit-count arrays the decoder reads
     const OffsetsExtra extra{nullptr, 0, 0, 0, 0, nullptr, nullptr, c->flag.as<uint32_t>(), c->bac_bits.as<uint32_t>(),
-                             c->byp_bits.as<uint32_t>(), nbytes, eae_coder_capacity_bytes(hw3, L) * 8u};
+                             c->byp_bits.as<uint32_t>(), nullptr, nbytes, eae_coder_capacity_bytes(hw3, L) * 8u};
     stream_offsets_kernel<<<1, 1024, 0, cs>>>(tbl, tbl + 1, 2, n_streams, kHeaderBytes + 8ull * n_streams,
                                               c->bac_off.as<uint64_t>(), c->byp_off.as<uint64_t>(),
                                               c->total_bytes.as<uint64_t>(), extra);
@@ -1189,6 +1196,14 @@ extern "C" int eae_decompress_dev(eae_codec_t* c, const eae_coding_params_t* prm
     EAE_CUDA_OK(cudaSetDevice(c->device));
     c->last_stream = (cudaStream_t)stream;
     return decompress_dev_impl(c, prm, container_dev, container_bytes, n, h, w, rec_dev, (cudaStream_t)stream);
+}
+
+extern "C" int eae_codec_set_stats_accumulator(eae_codec_t* c, eae_batch_stats_t* acc_dev)
+{
+    if (!c) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    c->stats_acc = acc_dev;
+    c->generation++;        // (the pointer is baked into captured steps)
+    return 0;
 }
 
 // Status of the device-resident entry points since the last poll (they cannot report device-side failures themselves).

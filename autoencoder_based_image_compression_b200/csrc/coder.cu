@@ -384,42 +384,108 @@ __global__ void transpose_i16_kernel(const int16_t* __restrict__ in, int16_t* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// Histograms of int16 symbols per map (tools.py count_symbols :322-388 on indices).
-// hist id of element (img, pix, map): per_image ? img * C + map : map.
-__global__ void minmax_abs_kernel(const int16_t* __restrict__ idx, uint64_t n_elems, uint32_t hw,
-                                  uint32_t C, int per_image, int32_t* __restrict__ mn,
-                                  int32_t* __restrict__ mx, unsigned long long* __restrict__ abs_sum)
+// Histograms of int16 symbols per map (tools.py count_symbols :322-388 on indices), on PLANAR streams
+// (stream s = image * C + map holds its `size` symbols contiguously: the layout the coder reads).
+// Warp-level kernels: one warp per stream, 16-byte loads (8 symbols per lane and instruction), no global atomics on
+// the way: extrema by warp shuffles, counts in a per-warp shared-memory histogram that is added to the result once.
+// hist id of stream s: per_image ? s : s % C.
+
+// The stream as 16-byte vectors where it is aligned, scalars before and after: f(symbol) for every symbol.
+template <typename F>
+__device__ __forceinline__ void for_each_symbol(const int16_t* __restrict__ src, uint32_t size, int lane, F f)
 {
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_elems;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t map = (uint32_t)(t % C);
-        const uint64_t img = t / ((uint64_t)hw * C);
-        const uint64_t j = per_image ? img * C + map : map;
-        const int v = idx[t];
-        atomicMin(&mn[j], v);
-        atomicMax(&mx[j], v);
-        if (abs_sum && v != 0) atomicAdd(&abs_sum[j], (unsigned long long)(v < 0 ? -v : v));
+    const uint32_t head = min(size, (uint32_t)(((16u - ((uint32_t)reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 1));
+    if ((uint32_t)lane < head) f((int)src[lane]);
+    const uint4* v = reinterpret_cast<const uint4*>(src + head);
+    const uint32_t nvec = (size - head) >> 3;
+    for (uint32_t i = lane; i < nvec; i += 32) {
+        const uint4 q = __ldg(v + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { f((int)(int16_t)(w[j] & 0xFFFFu)); f((int)(int16_t)(w[j] >> 16)); }
+    }
+    const uint32_t done = head + (nvec << 3);
+    if (done + lane < size) f((int)src[done + lane]);      // fewer than 8 symbols remain
+}
+
+__global__ void __launch_bounds__(256)
+stream_minmax_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint32_t size, int32_t* __restrict__ mn,
+                     int32_t* __restrict__ mx, unsigned long long* __restrict__ abs_sum)
+{
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_streams) return;
+    int lo = 32767, hi = -32768;
+    unsigned long long sum = 0;
+    for_each_symbol(idx + (size_t)s * size, size, lane, [&](int v) {
+        lo = v < lo ? v : lo; hi = v > hi ? v : hi; sum += (unsigned long long)(v < 0 ? -v : v);
+    });
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    }
+    if (lane == 0) { mn[s] = lo; mx[s] = hi; if (abs_sum) abs_sum[s] = sum; }
+}
+
+// Per-map extrema over all images (per_image == 0): thread = map.
+__global__ void reduce_over_images_kernel(const int32_t* __restrict__ mn_s, const int32_t* __restrict__ mx_s,
+                                          const unsigned long long* __restrict__ abs_s, uint32_t n_images, uint32_t C,
+                                          int32_t* __restrict__ mn, int32_t* __restrict__ mx,
+                                          unsigned long long* __restrict__ abs_sum)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= C) return;
+    int lo = 32767, hi = -32768;
+    unsigned long long sum = 0;
+    for (uint32_t i = 0; i < n_images; i++) {
+        lo = min(lo, mn_s[(size_t)i * C + m]); hi = max(hi, mx_s[(size_t)i * C + m]);
+        if (abs_s) sum += abs_s[(size_t)i * C + m];
+    }
+    mn[m] = lo; mx[m] = hi;
+    if (abs_sum) abs_sum[m] = sum;
+}
+
+// Dynamic shared memory: warps x cap counters. Symbols outside [mn, mn + cap) are not counted (the caller sizes cap).
+__global__ void __launch_bounds__(256)
+stream_hist_kernel(const int16_t* __restrict__ idx, uint32_t n_streams, uint32_t size, uint32_t C, int per_image,
+                   const int32_t* __restrict__ mn, unsigned long long* __restrict__ hist, uint32_t cap)
+{
+    extern __shared__ uint32_t counts[];
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_streams) return;      // (whole warps leave together; no block-wide barrier below)
+    uint32_t* mine = counts + (threadIdx.x >> 5) * cap;
+    for (uint32_t b = lane; b < cap; b += 32) mine[b] = 0;
+    __syncwarp();
+    const uint32_t j = per_image ? s : s % C;
+    const int lo = mn[j];
+    for_each_symbol(idx + (size_t)s * size, size, lane, [&](int v) {
+        const uint32_t b = (uint32_t)(v - lo);
+        if (b < cap) atomicAdd(&mine[b], 1u);
+    });
+    __syncwarp();
+    unsigned long long* dst = hist + (size_t)j * cap;
+    for (uint32_t b = lane; b < cap; b += 32) {
+        const uint32_t c = mine[b];
+        if (!c) continue;
+        if (per_image) dst[b] = c;                             // this warp is the only writer of histogram j
+        else atomicAdd(&dst[b], (unsigned long long)c);
     }
 }
 
-__global__ void hist_kernel(const int16_t* __restrict__ idx, uint64_t n_elems, uint32_t hw, uint32_t C,
-                            int per_image, const int32_t* __restrict__ mn,
-                            unsigned long long* __restrict__ hist, uint32_t cap)
+// Ranges too wide for a shared-memory histogram per warp: global atomics, thread = symbol.
+__global__ void stream_hist_wide_kernel(const int16_t* __restrict__ idx, uint64_t n_elems, uint32_t size, uint32_t C,
+                                        int per_image, const int32_t* __restrict__ mn,
+                                        unsigned long long* __restrict__ hist, uint32_t cap)
 {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_elems;
          t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t map = (uint32_t)(t % C);
-        const uint64_t img = t / ((uint64_t)hw * C);
-        const uint64_t j = per_image ? img * C + map : map;
+        const uint64_t s = t / size;
+        const uint64_t j = per_image ? s : s % C;
         const uint32_t b = (uint32_t)((int)idx[t] - mn[j]);
         if (b < cap) atomicAdd(&hist[j * cap + b], 1ull);
     }
-}
-
-__global__ void fill_i32_kernel(int32_t* p, uint64_t n, int32_t v)
-{
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
-         t += (uint64_t)gridDim.x * blockDim.x) p[t] = v;
 }
 
 // Byte offsets of the per-stream slots (decoder input when reading straight from the slot arenas).
@@ -483,6 +549,8 @@ static void coder_carveouts()
     if (!first_use_on_device(&seen)) return;
     prefer_max_shared(encode_streams3_kernel); prefer_max_shared(decode_streams3_kernel);
     prefer_max_shared(binarize_streams_kernel);
+    prefer_max_shared(stream_minmax_kernel); prefer_max_shared(stream_hist_kernel);
+    prefer_max_shared(reduce_over_images_kernel); prefer_max_shared(stream_hist_wide_kernel);
 }
 
 int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_t size,
@@ -504,11 +572,13 @@ int launch_encode_streams(const int16_t* idx_planar, uint32_t n_streams, uint32_
     uint32_t* ubits = nbins + n_streams;
     const uint32_t warps = 4;
     const size_t smem = (size_t)warps * (L + 2u + 34u) * 4;
+    ProfScope prof_binarize(kProfBinarize, st);
     if (!(probe_skip() & 1))
     binarize_streams_kernel<<<ceil_div_u32(n_streams, warps), warps * 32, smem, st>>>(
         idx_planar, n_streams, size, table_rows, L, skip_mask_dev, nbins, ubits, uwords, byp_slots, slot_bytes,
         byp_bits);
     EAE_LAUNCH_OK();
+    prof_binarize.close();
     const uint32_t lanes = lanes_v2(n_streams, lanes_req);
     const uint32_t group = (n_streams % table_rows == 0) ? n_streams / table_rows : 0u;
     const uint64_t threads = (uint64_t)n_streams * lanes;
@@ -560,27 +630,49 @@ int launch_slot_offsets(uint64_t* off, uint32_t n, uint32_t slot_bytes, cudaStre
     return 0;
 }
 
-int launch_histograms(const int16_t* idx_nhwc_dev, uint32_t n_images, uint32_t hw, uint32_t C,
+int launch_histograms(const int16_t* idx_planar_dev, uint32_t n_images, uint32_t hw, uint32_t C,
                       int per_image, int32_t* mn, int32_t* mx, unsigned long long* abs_sum,
                       unsigned long long* hist, uint32_t cap, bool only_minmax, cudaStream_t st)
 {
-    const uint64_t n_elems = (uint64_t)n_images * hw * C;
-    const uint64_t n_hist = per_image ? (uint64_t)n_images * C : C;
-    if (n_elems == 0) return 0;
-    const uint32_t grid = (uint32_t)((n_elems + 255) / 256 < 148u * 16u ? (n_elems + 255) / 256 : 148u * 16u);
+    const uint32_t n_streams = n_images * C;
+    const uint64_t n_hist = per_image ? (uint64_t)n_streams : C;
+    if (n_streams == 0 || hw == 0) return 0;
+    coder_carveouts();
+    ProfScope prof(kProfHist, st);
     if (only_minmax) {
-        fill_i32_kernel<<<ceil_div_u32(n_hist, 256), 256, 0, st>>>(mn, n_hist, 32767);
+        if (per_image) {
+            stream_minmax_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, st>>>(idx_planar_dev, n_streams, hw, mn, mx, abs_sum);
+            EAE_LAUNCH_OK();
+            return 0;
+        }
+        // per stream first, then per map over the images
+        int32_t* tmp = nullptr;
+        EAE_CUDA_OK(cudaMallocAsync(&tmp, (size_t)n_streams * 16, st));
+        int32_t* mn_s = tmp;
+        int32_t* mx_s = tmp + n_streams;
+        unsigned long long* abs_s = reinterpret_cast<unsigned long long*>(tmp + 2 * (size_t)n_streams);
+        stream_minmax_kernel<<<ceil_div_u32((uint64_t)n_streams * 32, 256), 256, 0, st>>>(idx_planar_dev, n_streams, hw, mn_s, mx_s,
+                                                                                         abs_sum ? abs_s : nullptr);
         EAE_LAUNCH_OK();
-        fill_i32_kernel<<<ceil_div_u32(n_hist, 256), 256, 0, st>>>(mx, n_hist, -32768);
+        reduce_over_images_kernel<<<ceil_div_u32(C, 128), 128, 0, st>>>(mn_s, mx_s, abs_sum ? abs_s : nullptr, n_images, C, mn, mx, abs_sum);
         EAE_LAUNCH_OK();
-        if (abs_sum) EAE_CUDA_OK(cudaMemsetAsync(abs_sum, 0, n_hist * sizeof(unsigned long long), st));
-        minmax_abs_kernel<<<grid, 256, 0, st>>>(idx_nhwc_dev, n_elems, hw, C, per_image, mn, mx, abs_sum);
-        EAE_LAUNCH_OK();
-    } else {
-        EAE_CUDA_OK(cudaMemsetAsync(hist, 0, n_hist * cap * sizeof(unsigned long long), st));
-        hist_kernel<<<grid, 256, 0, st>>>(idx_nhwc_dev, n_elems, hw, C, per_image, mn, hist, cap);
-        EAE_LAUNCH_OK();
+        EAE_CUDA_OK(cudaFreeAsync(tmp, st));
+        return 0;
     }
+    EAE_CUDA_OK(cudaMemsetAsync(hist, 0, n_hist * cap * sizeof(unsigned long long), st));
+    // as many warps per CTA as fit 48 KB of counters (no opt-in needed); beyond 12 288 bins: global atomics
+    uint32_t warps = cap ? (48u * 1024u) / (cap * 4u) : 8u;
+    if (warps > 8u) warps = 8u;
+    if (warps == 0u) {
+        const uint64_t n_elems = (uint64_t)n_streams * hw;
+        const uint32_t grid = (uint32_t)((n_elems + 255) / 256 < 148u * 16u ? (n_elems + 255) / 256 : 148u * 16u);
+        stream_hist_wide_kernel<<<grid, 256, 0, st>>>(idx_planar_dev, n_elems, hw, C, per_image, mn, hist, cap);
+        EAE_LAUNCH_OK();
+        return 0;
+    }
+    stream_hist_kernel<<<ceil_div_u32(n_streams, warps), warps * 32, (size_t)warps * cap * 4, st>>>(
+        idx_planar_dev, n_streams, hw, C, per_image, mn, hist, cap);
+    EAE_LAUNCH_OK();
     return 0;
 }
 
@@ -843,6 +935,18 @@ extern "C" int eae_compress_lossless_maps_host(const int16_t* ref_hwc, uint32_t 
     return 0;
 }
 
+extern "C" int eae_histogram_streams_dev(const int16_t* idx_planar_dev, uint32_t n_images, uint32_t size, uint32_t nb_maps,
+                                         int per_image, int32_t* min_dev, int32_t* max_dev, uint64_t* abs_sum_dev,
+                                         uint64_t* hist_dev, uint32_t hist_cap, void* stream)
+{
+    if (!idx_planar_dev || !min_dev || (!hist_dev && !max_dev)) { set_error("NULL pointer"); return EAE_ERR_NULL; }
+    if (hist_dev && hist_cap == 0) { set_error("hist_cap is 0"); return EAE_ERR_ARGUMENT; }
+    EAE_TRY(require_device());
+    return launch_histograms(idx_planar_dev, n_images, size, nb_maps, per_image, min_dev, max_dev,
+                             reinterpret_cast<unsigned long long*>(abs_sum_dev), reinterpret_cast<unsigned long long*>(hist_dev),
+                             hist_cap, hist_dev == nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int eae_histogram_maps_host(const int16_t* idx_nhwc, uint32_t n_images, uint32_t h, uint32_t w,
                                        uint32_t nb_maps, int per_image, int32_t* min_out, int32_t* max_out,
                                        uint64_t* hist_out, uint32_t hist_cap, uint32_t* needed_cap,
@@ -857,12 +961,15 @@ extern "C" int eae_histogram_maps_host(const int16_t* idx_nhwc, uint32_t n_image
     const uint32_t hw = h * w;
     const uint64_t n_elems = (uint64_t)n_images * hw * nb_maps;
     const uint64_t n_hist = per_image ? (uint64_t)n_images * nb_maps : nb_maps;
-    DevBuf idx, mn, mx, as, hist;
+    DevBuf nhwc, idx, mn, mx, as, hist;
+    EAE_TRY(nhwc.alloc(n_elems * 2));
     EAE_TRY(idx.alloc(n_elems * 2));
     EAE_TRY(mn.alloc(n_hist * 4));
     EAE_TRY(mx.alloc(n_hist * 4));
     EAE_TRY(as.alloc(n_hist * 8));
-    EAE_CUDA_OK(cudaMemcpyAsync(idx.p, idx_nhwc, n_elems * 2, cudaMemcpyHostToDevice, st));
+    EAE_CUDA_OK(cudaMemcpyAsync(nhwc.p, idx_nhwc, n_elems * 2, cudaMemcpyHostToDevice, st));
+    // planar streams [image * nb_maps + map][h * w]: the layout the warp-level kernels (and the coder) read
+    EAE_TRY(launch_transpose_i16(nhwc.as<int16_t>(), idx.as<int16_t>(), n_images, hw, nb_maps, st));
     EAE_TRY(launch_histograms(idx.as<int16_t>(), n_images, hw, nb_maps, per_image, mn.as<int32_t>(),
                               mx.as<int32_t>(), as.as<unsigned long long>(), nullptr, 0, true, st));
     EAE_CUDA_OK(cudaMemcpyAsync(min_out, mn.p, n_hist * 4, cudaMemcpyDeviceToHost, st));

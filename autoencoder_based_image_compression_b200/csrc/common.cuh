@@ -68,12 +68,13 @@ struct DevBuf {
 // Kernel classes of the optional device-side profile (eae_profile_*).
 enum ProfClass : int {
     kProfGemmConv = 0, kProfGemmTconv, kProfGemmGdn, kProfGemmThin, kProfIm2col, kProfCol2im, kProfQuantize,
-    kProfDequantize, kProfCoderEncode, kProfCoderDecode, kProfPack, kProfCount
+    kProfDequantize, kProfCoderEncode, kProfCoderDecode, kProfPack, kProfBinarize, kProfHist, kProfCount
 };
 // Brackets the launches issued during its lifetime with a CUDA event pair when profiling is on.
 struct ProfScope {
     ProfScope(int cls, cudaStream_t st);
     ~ProfScope();
+    void close();      // ends the scope early (scopes may nest: a class can be a part of another)
     int slot;
     cudaStream_t stream;
 };

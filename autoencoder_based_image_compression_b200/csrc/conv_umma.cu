@@ -207,7 +207,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.out = plan.out; q.bias = plan.bias; q.beta = plan.fuse_beta;
         q.Hout = plan.Hout; q.Wout = plan.Wout; q.out_mul = plan.out_mul; q.out_r = plan.out_r; q.out_s = plan.out_s;
         q.out_split = plan.out_split;
-        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0; q.exact_gdn = plan.fuse_single_pass ? 0 : 1; q.precise_gdn = plan.fuse_precise;
+        q.fuse = plan.fuse; q.exact_main = exact3x ? 1 : 0; q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
         q.idx_out = plan.quant_idx; q.q_mean = plan.quant_mean; q.q_delta = plan.quant_delta; q.q_flag = plan.quant_flag;
         q.error_flag = g_error_flag;
         // groups = input planes in use; taps sorted by group
@@ -282,11 +282,17 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
                 EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
             }
+            // four instantiations: {MUFU, IEEE} normalisation x {fp32 pixels, quantizer} store
+            typedef void (*Kernel4)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                    const UmmaParams4x);
+            static const Kernel4 kernels4[4] = {gemm_umma4_kernel<false, false>, gemm_umma4_kernel<true, false>,
+                                                gemm_umma4_kernel<false, true>, gemm_umma4_kernel<true, true>};
             static bool attr4_done = false;
             if (!attr4_done) {
-                EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
+                for (Kernel4 k : kernels4) EAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
                 attr4_done = true;
             }
+            const Kernel4 kernel4 = kernels4[(plan.fuse && plan.fuse_precise ? 1 : 0) + (plan.quant_idx ? 2 : 0)];
             const uint32_t grid4 = n_img * (uint32_t)(q.tiles_x * q.tiles_y) * (uint32_t)qx.n_phases;
             static int timing4 = -1;
             if (timing4 < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing4 = e ? atoi(e) : 0; }
@@ -303,7 +309,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * 12 * sizeof(long long), st));
                 for (int i = 0; i < qx.n_phases; i++) qx.ph[i].times = d_times;
             }
-            gemm_umma4_kernel<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
+            kernel4<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
             EAE_LAUNCH_OK();
             if (timing4) {
                 std::vector<long long> h((size_t)grid4 * 12);
@@ -358,7 +364,6 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         q.fuse = plan.fuse;
         q.exact_main = exact3x ? 1 : 0;
         q.exact_gdn = plan.fuse_single_pass ? 0 : 1;
-        q.precise_gdn = plan.fuse_precise;
         q.error_flag = p.error_flag;
         memcpy(q.taps, p.taps, sizeof q.taps);
         const uint32_t grid3 = n_img * (uint32_t)(q.tiles_x * q.tiles_y);
@@ -376,11 +381,16 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             q.conv1 = 1;
             EAE_TRY(make_map_u8(&map_img, plan.img_u8, (uint64_t)plan.img_W, (uint64_t)plan.img_H, n_img));
         }
+        typedef void (*Kernel3)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                const CUtensorMap, const UmmaParams3);
+        static const Kernel3 kernels3[3] = {gemm_umma3_kernel<false, false>, gemm_umma3_kernel<true, false>,
+                                            gemm_umma3_kernel<false, true>};
         static bool attr3_done = false;
         if (!attr3_done) {
-            EAE_CUDA_OK(cudaFuncSetAttribute(gemm_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
+            for (Kernel3 k : kernels3) EAE_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes3));
             attr3_done = true;
         }
+        const Kernel3 kernel3 = kernels3[plan.dequant_idx ? 2 : (plan.fuse && plan.fuse_precise ? 1 : 0)];
         static int timing = -1;
         if (timing < 0) { const char* e = getenv("EAE_UMMA_TIMING"); timing = (e && atoi(e) == 1) ? 1 : 0; }
         if (timing) {
@@ -389,7 +399,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid3 * 8 * sizeof(long long)));
             EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid3 * 8 * sizeof(long long), st));
             q.times = d_times;
-            gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
+            kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
             EAE_LAUNCH_OK();
             std::vector<long long> h((size_t)grid3 * 8);
             EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -409,7 +419,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                     acc[5] / grid3, acc[6] / grid3, acc[7] / grid3);
             return 0;
         }
-        gemm_umma3_kernel<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
+        kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
         EAE_LAUNCH_OK();
         return 0;
     }

@@ -27,7 +27,8 @@ int launch_prepare_table(const double* table_dev, uint32_t rows, uint32_t L, uin
 int launch_slot_offsets(uint64_t* off, uint32_t n, uint32_t slot_bytes, cudaStream_t st);
 int launch_transpose_i16(const int16_t* in, int16_t* out, uint32_t batch, uint32_t rows, uint32_t cols,
                          cudaStream_t st);
-int launch_histograms(const int16_t* idx_nhwc_dev, uint32_t n_images, uint32_t hw, uint32_t C,
+// (planar streams: stream image * C + map holds its hw symbols contiguously)
+int launch_histograms(const int16_t* idx_planar_dev, uint32_t n_images, uint32_t hw, uint32_t C,
                       int per_image, int32_t* mn, int32_t* mx, unsigned long long* abs_sum,
                       unsigned long long* hist, uint32_t cap, bool only_minmax, cudaStream_t st);
 

@@ -68,12 +68,15 @@ ProfScope::ProfScope(int cls, cudaStream_t st) : slot(-1), stream(st)
     slot = (int)g_prof_events.size() - 1;
 }
 
-ProfScope::~ProfScope()
+void ProfScope::close()
 {
     if (slot < 0) return;
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     cudaEventRecord(g_prof_events[slot].b, stream);
+    slot = -1;
 }
+
+ProfScope::~ProfScope() { close(); }
 
 static void prof_drain()
 {
@@ -134,7 +137,7 @@ extern "C" int eae_profile_read(int cls, uint64_t* launches, double* total_ms)
 extern "C" const char* eae_profile_name(int cls)
 {
     static const char* names[kProfCount] = {"gemm_conv", "gemm_tconv", "gemm_gdn", "gemm_thin", "im2col", "col2im",
-                                            "quantize", "dequantize", "coder_encode", "coder_decode", "pack"};
+                                            "quantize", "dequantize", "coder_encode", "coder_decode", "pack", "binarize", "hist"};
     return (cls >= 0 && cls < kProfCount) ? names[cls] : "";
 }
 

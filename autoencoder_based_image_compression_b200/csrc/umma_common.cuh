@@ -161,7 +161,6 @@ struct UmmaParams3 {
     int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
     int exact_main;          // 3xTF32 for the main contraction
     int exact_gdn;           // 3xTF32 for the fused norm (versions 3 and 4)
-    int precise_gdn;         // IEEE sqrt / division in the fused normalisation (GemmPlan::fuse_precise)
     int tile_w_log2;
     int half_da, half_db;    // version 3: offset of the second 128-row half of a tile in the position grid
     int conv1;               // version 3: A rows are the 9x9 patches (k9 s4) of a uint8 image tile staged by TMA

@@ -43,7 +43,7 @@ struct UmmaParams4 {
     const float* bias;
     const float* beta;
     int Hout, Wout, out_mul, out_r, out_s, out_split;
-    int fuse, exact_main, exact_gdn, precise_gdn;
+    int fuse, exact_main, exact_gdn;
     int16_t* idx_out;         // quantizer fused into the store (see OutGeom4), or NULL
     const float* q_mean;
     const float* q_delta;
@@ -63,6 +63,8 @@ struct UmmaParams4x {
     UmmaParams4 ph[4];
 };
 
+// kPrecise: IEEE normalisation in the fused tail; kQuant: the store is the quantizer (OutGeom4::idx_out)
+template <bool kPrecise, bool kQuant>
 __global__ void __maxnreg__(kMaxRegs34)
 gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
@@ -83,7 +85,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
     const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
-                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn, p.precise_gdn};
+                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -272,7 +274,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         uint8_t* stage0 = smem;                          // un-fused epilogue: both halves staged side by side
         uint8_t* stage1 = smem + kGdnStageBytes4;
         if (ok && n_gdn) {
-            ok = gdn_tail_ts_run(tail, set, row, lane, wq, lane_base, p.fuse, p.bias, p.beta, geom, p.error_flag, stamp);
+            ok = gdn_tail_ts_run<kPrecise, kQuant>(tail, set, row, lane, wq, lane_base, p.fuse, p.bias, p.beta, geom, p.error_flag, stamp);
         } else {
             if (ok) ok = mbar_wait(acc_full, 0, p.error_flag, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -280,8 +282,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             stage_tile(smem, kGdnStageBytes4, lane_base, set, row, false, 0, p.bias, p.beta);
             named_bar_sync(1, 256);     // both sets finished staging
             if (stamp && threadIdx.x == 64) stamp[6] = clock64();
-            store_half4(geom, stage0, 0, wq, lane, ok);
-            store_half4(geom, stage1, 1, wq, lane, ok);
+            store_half4<kQuant>(geom, stage0, 0, wq, lane, ok);
+            store_half4<kQuant>(geom, stage1, 1, wq, lane, ok);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

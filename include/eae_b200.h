@@ -165,6 +165,15 @@ int eae_histogram_maps_host(const int16_t* idx_nhwc, uint32_t n_images, uint32_t
                             uint64_t* hist_out, uint32_t hist_cap, uint32_t* needed_cap,
                             uint64_t* abs_sum_out, void* stream);
 
+/* The same on device-resident PLANAR streams (stream image * nb_maps + map holds its `size` symbols contiguously: the
+ * layout the codec and the coder primitives below use), asynchronous, warp-level (one warp per stream, 16-byte loads,
+ * counts in shared memory). Two calls: with hist_dev == NULL it writes min_dev / max_dev (and abs_sum_dev if given);
+ * with hist_dev != NULL it reads min_dev and writes the counts (hist_cap bins per histogram, zeroed first; symbols
+ * beyond min + hist_cap are not counted). Number of histograms: per_image ? n_images * nb_maps : nb_maps. */
+int eae_histogram_streams_dev(const int16_t* idx_planar_dev, uint32_t n_images, uint32_t size, uint32_t nb_maps,
+                              int per_image, int32_t* min_dev, int32_t* max_dev, uint64_t* abs_sum_dev,
+                              uint64_t* hist_dev, uint32_t hist_cap, void* stream);
+
 /* ---- device-level coder primitives (planar streams: stream s holds `size` int16 at s * size) ---- */
 
 /* Bytes of one per-stream slot in the scratch arenas (capacity rounded up to 16). */
@@ -358,6 +367,12 @@ int eae_compress_dev(eae_codec_t* codec, const eae_coding_params_t* params, cons
 int eae_decompress_dev(eae_codec_t* codec, const eae_coding_params_t* params, const uint8_t* container_dev,
                        uint64_t container_bytes, uint32_t n, uint32_t h, uint32_t w, uint8_t* reconstruction_dev,
                        void* stream);
+
+/* Running totals over steps: when set (device pointer, caller-owned, zeroed by the caller; NULL to stop), every
+ * eae_compress_* step of this codec also ADDS its statistics to *acc_dev with atomic adds, so several codecs (pipeline
+ * slots) may share one accumulator and a multi-GPU job reduces it ONCE at the end, as the reference does
+ * (reconstructing_eae_kodak.py:810-815), instead of once per batch. */
+int eae_codec_set_stats_accumulator(eae_codec_t* codec, eae_batch_stats_t* acc_dev);
 
 /* What the device-resident steps of this codec recorded since the previous poll (sticky), plus the decoder's error of
  * the LAST eae_decompress_dev step. Enqueues a one-CTA kernel on `stream`, waits for the stream, clears the record.

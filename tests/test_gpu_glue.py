@@ -132,3 +132,35 @@ def test_save_statistics_writes_the_three_kinds_of_files(stats, native, tmp_path
         assert numpy.array_equal(table, want)
     with pytest.raises(ValueError):      # stats.py:296-297
         stats.save_statistics(lum, None, entropy_ae, 2, multipliers, 10, p_mean, p_idx, paths[:1])
+
+
+@pytest.mark.parametrize('per_image', [1, 0])
+def test_warp_level_histograms_of_planar_streams(native, per_image):
+    """eae_histogram_streams_dev (one warp per stream, 16-byte loads, shared-memory counters) against numpy, on stream
+    lengths that are and are not multiples of the vector width (so streams start at every 2-byte alignment), a range
+    wider than one shared-memory histogram (global-atomics kernel) and a constant map. tools.py:322-388."""
+    import torch
+    lib = native.lib()
+    rng = numpy.random.default_rng(31)
+    dev = torch.device('cuda', 0)
+    for (n_images, size, C, spread) in ((3, 1536, 128, 6.), (2, 1537, 5, 40.), (4, 3, 7, 2.), (1, 32400, 16, 3000.), (2, 77, 4, 0.)):
+        idx = numpy.round(rng.laplace(0., 1., size=(n_images, C, size))*spread).clip(-32768, 32767).astype(numpy.int16)
+        d_idx = torch.from_numpy(idx).to(dev)
+        n_hist = n_images*C if per_image else C
+        d_mn = torch.zeros(n_hist, dtype=torch.int32, device=dev)
+        d_mx = torch.zeros(n_hist, dtype=torch.int32, device=dev)
+        d_abs = torch.zeros(n_hist, dtype=torch.int64, device=dev)
+        native.check(lib.eae_histogram_streams_dev(d_idx.data_ptr(), n_images, size, C, per_image, d_mn.data_ptr(),
+                                                   d_mx.data_ptr(), d_abs.data_ptr(), None, 0, None))
+        grouped = idx.reshape(n_hist, size) if per_image else idx.transpose(1, 0, 2).reshape(C, n_images*size)
+        assert numpy.array_equal(d_mn.cpu().numpy(), grouped.min(axis=1))
+        assert numpy.array_equal(d_mx.cpu().numpy(), grouped.max(axis=1))
+        assert numpy.array_equal(d_abs.cpu().numpy(), numpy.abs(grouped.astype(numpy.int64)).sum(axis=1))
+        cap = int((grouped.max(axis=1).astype(numpy.int64) - grouped.min(axis=1)).max()) + 1
+        d_hist = torch.full((n_hist, cap), -1, dtype=torch.int64, device=dev)
+        native.check(lib.eae_histogram_streams_dev(d_idx.data_ptr(), n_images, size, C, per_image, d_mn.data_ptr(),
+                                                   None, None, d_hist.data_ptr(), cap, None))
+        hist = d_hist.cpu().numpy()
+        for j in range(n_hist):
+            want = numpy.bincount(grouped[j].astype(numpy.int64) - int(grouped[j].min()), minlength=cap)
+            assert numpy.array_equal(hist[j], want), (n_images, size, C, j)
