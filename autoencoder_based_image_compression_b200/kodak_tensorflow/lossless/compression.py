@@ -2,6 +2,7 @@
 (kodak_tensorflow/lossless/compression.py:11-154): all maps of a latent are coded as independent GPU
 streams in one launch instead of 127 FFI calls."""
 import ctypes
+import os
 
 import numpy
 
@@ -12,12 +13,17 @@ _TABLE_CACHE = {}
 
 
 def _load_table(path_to_binary_probabilities, nb_maps):
-    # The reference re-loads the .npy for every image (compression.py:60); the table is tiny and
-    # immutable, so it is cached per path.
-    table = _TABLE_CACHE.get(path_to_binary_probabilities)
+    # The reference re-loads the .npy for every image (compression.py:60). The table is tiny; it is cached per path AND
+    # file identity (modification time, size), so that statistics regenerated in the same process (stats.save_statistics
+    # tells the user to delete the files to recompute them) are picked up as the reference would pick them up.
+    st = os.stat(path_to_binary_probabilities)
+    key = (path_to_binary_probabilities, st.st_mtime_ns, st.st_size)
+    table = _TABLE_CACHE.get(key)
     if table is None:
         table = numpy.load(path_to_binary_probabilities)
-        _TABLE_CACHE[path_to_binary_probabilities] = table
+        for stale in [k for k in _TABLE_CACHE if k[0] == path_to_binary_probabilities]:
+            del _TABLE_CACHE[stale]
+        _TABLE_CACHE[key] = table
     if table.ndim != 2:
         raise ValueError('`binary_probabilities.ndim` is not equal to 2.')
     if table.shape[0] != nb_maps:

@@ -1,7 +1,10 @@
 """Per-layer table of the tap-list GEMM launches of one bench step from an ``ncu --set full`` capture.
 
     ncu -i gpurun_out/prof_rXX_gemm.ncu-rep --page raw --csv > raw.csv
-    python scripts/ncu_gemm_layers.py raw.csv "title" [images] [math] > profiles/rXX_ncu_full_gemm_layers.md
+    python scripts/ncu_gemm_layers.py raw.csv "title" [images] [math] [traffic.json] > profiles/rXX_ncu_full_gemm_layers.md
+
+The capture may start anywhere in a step (take -c 26): the table starts at the first launch after a last-layer launch.
+traffic.json (optional) receives the DRAM bytes of the step, which bench.py reads for `roofline.traffic`.
 
 math = tf32x3 (3 MMAs per product everywhere) or mixed (synthesis side: one MMA per product, fused IGDN norms too).
 """
@@ -51,7 +54,13 @@ def main():
           'algorithmic TFLOP/s | executed-MMA TFLOP/s |')
     print('|---|---|---|---|---|---|---|---|---|')
     (tt, tr, tw, ta, te) = (0., 0., 0., 0., 0.)
-    for (k, r) in enumerate(rows[2:2 + len(NAMES)]):
+    body = rows[2:]
+    start = 0
+    for (k, r) in enumerate(body):          # a step starts right after the persistent last-layer kernel of the previous one
+        if 'umma7' in r[c['Kernel Name']] and k + 1 + len(NAMES) <= len(body):
+            start = k + 1
+            break
+    for (k, r) in enumerate(body[start:start + len(NAMES)]):
         d = float(r[c['gpu__time_duration.sum']])
         rd = float(r[c['dram__bytes_read.sum']])
         wr = float(r[c['dram__bytes_write.sum']])
@@ -70,6 +79,12 @@ def main():
         tt, tr, tw, ta/tt*1e3, te/tt*1e3))
     print()
     print('DRAM traffic of the 13 launches: {:.0f} MB per step = {:.1f} MB per launch on average.'.format(tr + tw, (tr + tw)/13.))
+    if len(sys.argv) > 5:
+        import json
+        with open(sys.argv[5], 'w') as f:
+            json.dump({'math': sys.argv[4], 'images': images, 'launches_per_step': len(NAMES), 'dram_bytes_per_step': (tr + tw)*1e6,
+                       'source': 'ncu --set full capture summarised by scripts/ncu_gemm_layers.py (dram__bytes_read.sum + dram__bytes_write.sum of the 13 tap-list GEMM launches of one step)'}, f)
+            f.write('\n')
 
 
 if __name__ == '__main__':

@@ -26,7 +26,7 @@ def _worker(rank, world, port, nb_images, out_dir):
     for i in range(a, b):
         bits += (i + 1)*numpy.arange(1, 129)
         sse += 10.*(i + 1)
-    vec = parallel.pack_stats(bits, bits.sum(), rank, sse, (b - a)*64, b - a)
+    vec = parallel.pack_stats(bits, bits.sum(), rank, sse, (b - a)*64, b - a, sum(30. + i for i in range(a, b)))
     total = parallel.all_reduce_stats(vec)
     slowest = parallel.max_over_ranks(1.5 + rank)
     numpy.save(os.path.join(out_dir, 'rank{}.npy'.format(rank)), numpy.append(total, slowest))
@@ -43,4 +43,6 @@ def test_two_rank_shard_and_reduce(tmp_path):
     assert numpy.array_equal(stats['bits_per_map'], tri*numpy.arange(1, 129))
     assert stats['nb_images'] == nb_images and stats['nb_pixels'] == nb_images*64
     assert stats['sum_squared_error'] == 10.*tri and stats['nb_dead_maps'] == 1
+    # mean of the per-image PSNRs over both ranks, as numpy.mean(psnr, axis=1) gives it in the reference
+    assert parallel.summarize(stats)['psnr_db'] == sum(30. + i for i in range(nb_images))/nb_images
     assert results[0][-1] == 2.5
