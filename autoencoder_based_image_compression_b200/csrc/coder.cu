@@ -272,14 +272,23 @@ __device__ __forceinline__ void decode_prefixes_fast(const T* __restrict__ mrow,
         k = done ? 0u : k + 1u;
         mul = done ? m0 : up;
     }
+    k = a;      // (a and k never differ: both count the ones of the current symbol; the checked loop below uses k)
     while (i < size) {
         const uint32_t bit = core::fast_decode_bin<true>(st, bac, mul);
-        a += bit;
         const bool done = !bit || k == L - 1u;
-        if (done) { dst[i] = (int16_t)a; i++; a = 0; }
+        if (done) { dst[i] = (int16_t)(k + bit); i++; }
         k = done ? 0u : k + 1u;
         mul = Mul{__ldg(mrow + k)};
     }
+}
+
+// Decoder phase B for one symbol whose prefix decoded to a0 != 0: Exp-Golomb suffix and sign from the bypass stream.
+__device__ __forceinline__ uint32_t bypass_symbol(uint32_t a0, uint32_t L, core::BitSource& byp, int16_t* __restrict__ dst)
+{
+    int v;
+    const uint32_t eb = core::lean_decode_bypass(a0, L, byp, v);
+    if (!eb) *dst = (int16_t)v;
+    return eb;
 }
 
 __global__ void __launch_bounds__(256)
@@ -333,17 +342,39 @@ decode_streams3_kernel(int16_t* __restrict__ out, uint32_t n_streams, uint32_t s
         if (flags & 2u) decode_prefixes_fast<core::MulFixed48>(qtable + (size_t)row * L, L, size, bac, dst);
         else decode_prefixes_fast<core::MulFp64>(prow, L, size, bac, dst);
     }
-    // phase B: EG0 suffixes and signs from the bypass stream
+    // phase B: EG0 suffixes and signs from the bypass stream. The magnitudes come back from global memory, where phase A
+    // left them (an L2 round trip of ~300 cycles per read when they are fetched one by one: a quarter of the kernel on
+    // peaked maps): eight per 16-byte load, the next eight requested while these are worked on; all-zero groups are skipped.
     core::BitSource byp;
     byp.init(byp_base + byp_off[s], byp_bits[s]);
-    for (uint32_t i = 0; i < n_ok; i++) {
+    uint32_t eb = 0;      // (an error of phase A stands unless the bypass stream fails first, as in the one-by-one loop)
+    uint32_t i = 0;
+    const uint32_t head = min(n_ok, (uint32_t)(((16u - ((uint32_t)reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 1));
+    for (; i < head && !eb; i++) {
         const uint32_t a0 = (uint32_t)(uint16_t)dst[i];
-        if (a0 == 0u) continue;
-        int v;
-        const uint32_t eb = core::lean_decode_bypass(a0, L, byp, v);
-        if (eb) { e = eb; break; }
-        dst[i] = (int16_t)v;
+        if (a0) eb = bypass_symbol(a0, L, byp, dst + i);
     }
+    uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+    if (i + 8u <= n_ok) cur = *reinterpret_cast<const uint4*>(dst + i);
+    while (i + 8u <= n_ok && !eb) {
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 16u <= n_ok) nxt = *reinterpret_cast<const uint4*>(dst + i + 8u);
+        if (cur.x | cur.y | cur.z | cur.w) {
+            const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+            #pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t a0 = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                if (a0 && !eb) eb = bypass_symbol(a0, L, byp, dst + i + j);
+            }
+        }
+        cur = nxt;
+        i += 8u;
+    }
+    for (; i < n_ok && !eb; i++) {
+        const uint32_t a0 = (uint32_t)(uint16_t)dst[i];
+        if (a0) eb = bypass_symbol(a0, L, byp, dst + i);
+    }
+    if (eb) e = eb;
     err[s] = e;
 }
 

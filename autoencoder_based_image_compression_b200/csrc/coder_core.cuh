@@ -712,5 +712,6 @@ EAE_HD uint32_t fast_decode_bin(DecState& s, FastSource& bac, const Mul& mul)
     return bit;
 }
 
+
 }  // namespace core
 }  // namespace eae

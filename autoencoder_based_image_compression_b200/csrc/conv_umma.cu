@@ -304,22 +304,22 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 if (d_times_cap < grid4) {
                     if (d_times) cudaFree(d_times);
                     d_times_cap = grid4 > 8192 ? grid4 : 8192;
-                    EAE_CUDA_OK(cudaMalloc(&d_times, d_times_cap * 12 * sizeof(long long)));
+                    EAE_CUDA_OK(cudaMalloc(&d_times, d_times_cap * kStamps4 * sizeof(long long)));
                 }
-                EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * 12 * sizeof(long long), st));
+                EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * kStamps4 * sizeof(long long), st));
                 for (int i = 0; i < qx.n_phases; i++) qx.ph[i].times = d_times;
             }
             kernel4<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
             EAE_LAUNCH_OK();
             if (timing4) {
-                std::vector<long long> h((size_t)grid4 * 12);
+                std::vector<long long> h((size_t)grid4 * kStamps4);
                 EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
                 EAE_CUDA_OK(cudaStreamSynchronize(st));
                 double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (uint32_t b = 0; b < grid4; b++)
-                    for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 12 + j] - h[(size_t)b * 12]);
+                    for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * kStamps4 + j] - h[(size_t)b * kStamps4]);
                 std::vector<long long> dur(grid4);
-                for (uint32_t b = 0; b < grid4; b++) dur[b] = h[(size_t)b * 12 + 7] - h[(size_t)b * 12];
+                for (uint32_t b = 0; b < grid4; b++) dur[b] = h[(size_t)b * kStamps4 + 7] - h[(size_t)b * kStamps4];
                 std::sort(dur.begin(), dur.end());
                 // which SMs ran the CTAs, and when (global timer): makespan against the busy time of the SMs
                 {
@@ -327,15 +327,31 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                     long long t_min = h[8], t_max = h[9];
                     double busy_ns = 0.;
                     for (uint32_t b = 0; b < grid4; b++) {
-                        per_sm[h[(size_t)b * 12 + 10] & 255]++;
-                        if (h[(size_t)b * 12 + 8] < t_min) t_min = h[(size_t)b * 12 + 8];
-                        if (h[(size_t)b * 12 + 9] > t_max) t_max = h[(size_t)b * 12 + 9];
-                        busy_ns += (double)(h[(size_t)b * 12 + 9] - h[(size_t)b * 12 + 8]);
+                        per_sm[h[(size_t)b * kStamps4 + 10] & 255]++;
+                        if (h[(size_t)b * kStamps4 + 8] < t_min) t_min = h[(size_t)b * kStamps4 + 8];
+                        if (h[(size_t)b * kStamps4 + 9] > t_max) t_max = h[(size_t)b * kStamps4 + 9];
+                        busy_ns += (double)(h[(size_t)b * kStamps4 + 9] - h[(size_t)b * kStamps4 + 8]);
                     }
                     int used = 0, most = 0, least = 1 << 30;
                     for (int i = 0; i < 256; i++) if (per_sm[i]) { used++; most = per_sm[i] > most ? per_sm[i] : most; least = per_sm[i] < least ? per_sm[i] : least; }
                     fprintf(stderr, "umma4 grid %u: %d SMs used, %d..%d CTAs per SM, makespan %.1f us, CTA time summed / 148 = %.1f us\n",
                             grid4, used, least, most, (double)(t_max - t_min) * 1e-3, busy_ns * 1e-3 / 148.);
+                }
+                {
+                    // one conversion (set 0) and one MMA issue in the steady state of the main loop (iteration 8)
+                    double cv[6] = {0, 0, 0, 0, 0, 0}, mm[4] = {0, 0, 0, 0};
+                    uint32_t nb = 0;
+                    for (uint32_t b = 0; b < grid4; b++) {
+                        const long long* t = &h[(size_t)b * kStamps4];
+                        if (!t[12] || !t[18]) continue;
+                        nb++;
+                        for (int j = 0; j < 6; j++) cv[j] += (double)(t[12 + j] - t[12]);
+                        for (int j = 0; j < 4; j++) mm[j] += (double)(t[18 + j] - t[12]);
+                    }
+                    if (nb)
+                        fprintf(stderr, "umma4 iteration 8 (cycles from the conversion's loop top): union seen %.0f, rows read %.0f, slot free %.0f, "
+                                        "slot written %.0f, arrived %.0f | MMA warp: loop top %.0f, slot seen %.0f, weights seen %.0f, issued %.0f\n",
+                                cv[1] / nb, cv[2] / nb, cv[3] / nb, cv[4] / nb, cv[5] / nb, mm[0] / nb, mm[1] / nb, mm[2] / nb, mm[3] / nb);
                 }
                 fprintf(stderr, "umma4 taps %d groups %d fuse %d grid %u: setup %.0f first_union %.0f acc_seen %.0f nrm_seen %.0f "
                                 "staged %.0f end %.0f (avg cycles from CTA start, conversion warp 2); CTA duration min %lld "

@@ -33,6 +33,7 @@ constexpr int kSmemBytes4 = kOffBars4 + 512 + 1024;
 constexpr int kGdnStageBytes4 = 4 * kTileBytes;
 static_assert(3 * kGdnStageBytes4 <= kOffBars4, "GDN / epilogue stages must fit below the barriers");
 constexpr int kMaxGroups4 = 4;
+constexpr int kStamps4 = 24;     // clock stamps per CTA (EAE_UMMA_TIMING=4): [0..7] phases, [8..10] timer / SM, [12..21] iteration 8
 
 struct UmmaTap4 { int w_tap, off, grp, last; };            // off: row offset of this tap's box inside its group's union
 struct UmmaGroup4 { int plane, fy, fx, pad; };             // union origin relative to the tile origin
@@ -75,13 +76,17 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars4);
-    uint64_t* b_full = bars;               // [4] weight stage landed
+    // (bars[0..3]: formerly one "weight stage landed" barrier per stage; the weights now complete the `split` barrier)
     uint64_t* done = bars + 4;             // [4] the MMAs of iteration it (it & 3) completed: ONE commit per iteration
                                            //     releases the weight stage (it + 4), the TMEM A slot (it + 2) and, after the
                                            //     last tap of a group, its union buffer (a tcgen05.commit costs ~100 cycles of
                                            //     tensor-pipe time, three per iteration made the loop 15 % slower)
     uint64_t* u_full = bars + 8;           // [2] union box landed
-    uint64_t* split = bars + 12;           // [4] TMEM A slot of iteration it (it & 3) written (one arrival per conversion warp)
+    uint64_t* split = bars + 12;           // [4] operands of iteration it (it & 3) ready: TMEM A slot written (one arrival per
+                                           //     conversion warp) AND weight stage landed (the producer's expect_tx arrival +
+                                           //     the TMA bytes): ONE wait per iteration in the MMA warp, whose barrier round
+                                           //     trips (~90 cycles each, measured) are not hidden by anything - a tcgen05.mma
+                                           //     occupies the issuing thread for about as long as it executes
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
     const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
@@ -89,7 +94,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * 12 : nullptr;      // [8] start ns, [9] end ns, [10] SM id
+    long long* stamp = p.times ? p.times + (size_t)blockIdx.x * kStamps4 : nullptr;      // [8] start ns, [9] end ns, [10] SM id
     if (stamp && threadIdx.x == 64) {
         stamp[0] = clock64();
         uint32_t smid;
@@ -105,9 +110,9 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 4; s++) { mbar_init(&b_full[s], 1); mbar_init(&done[s], 1); }
+        for (int s = 0; s < 4; s++) mbar_init(&done[s], 1);
         for (int s = 0; s < 2; s++) mbar_init(&u_full[s], 1);
-        for (int s = 0; s < 4; s++) mbar_init(&split[s], 4);      // one arrival per conversion warp
+        for (int s = 0; s < 4; s++) mbar_init(&split[s], 5);      // one arrival per conversion warp + the producer's
         gdn_tail_ts_init(tail);
         mbar_init(acc_full, 1);
         mbar_init(nrm_full, 1);
@@ -163,9 +168,9 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 const int s = it & 3;
                 if (!mbar_wait(&done[s], ((uint32_t)(it >> 2) & 1u) ^ 1u, p.error_flag, 0)) { ok = false; break; }
                 uint8_t* st = smem + kOffB4 + s * kBStageBytes4;
-                mbar_expect_tx(&b_full[s], (p.exact_main ? 2 : 1) * kTileBytes);
-                tma_load_3d(st, &map_b_hi, &b_full[s], kc * kChunkK, 0, tap.w_tap);
-                if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &b_full[s], kc * kChunkK, 0, tap.w_tap);
+                mbar_expect_tx(&split[s], (p.exact_main ? 2 : 1) * kTileBytes);
+                tma_load_3d(st, &map_b_hi, &split[s], kc * kChunkK, 0, tap.w_tap);
+                if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &split[s], kc * kChunkK, 0, tap.w_tap);
             }
             if (ok && n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
@@ -175,8 +180,12 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             bool ok = true;
             for (int it = 0; it < n_main && ok; it++) {
                 const int slot_i = it & 1, s = it & 3;
+                const bool probe = stamp && it == 8 && lane == 0;
+                if (probe) stamp[18] = clock64();
+                // (every lane polls: with one polling lane and a shuffle the compiler no longer proves the MMA operands
+                //  warp-uniform and the issue of every tcgen05.mma slows down by ~25 cycles - measured)
                 ok = mbar_wait(&split[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
-                if (ok) ok = mbar_wait(&b_full[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
+                if (probe) { stamp[19] = clock64(); stamp[20] = stamp[19]; }
                 ok = __all_sync(0xFFFFFFFFu, ok);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -201,6 +210,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                     }
                     umma_commit(&done[s]);
                     if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
+                    if (stamp && it == 8) stamp[21] = clock64();
                 }
                 __syncwarp();
             }
@@ -221,8 +231,11 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             const int kc = it / p.n_taps, t = it - kc * p.n_taps;
             const UmmaTap4 tap = p.taps[t];
             const int g = kc * p.n_groups + tap.grp;
+            const bool probe = stamp && it == 8 && threadIdx.x == 64;
+            if (probe) stamp[12] = clock64();
             ok = mbar_wait(&u_full[g & 1], (uint32_t)(g >> 1) & 1u, p.error_flag, 2);
             if (!ok) break;
+            if (probe) stamp[13] = clock64();
             if (stamp && it == 0 && threadIdx.x == 64) stamp[2] = clock64();
             // Read both halves' rows first: the shared-memory reads do not depend on the TMEM slot, so they overlap the
             // wait for the MMAs of iteration it - 2 (the completion -> conversion -> issue chain paces the loop).
@@ -240,11 +253,13 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 }
             }
             const uint32_t slot = slot_set + (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
+            if (probe) stamp[14] = clock64();
             if (it >= reuse) {
                 ok = mbar_wait(&done[(it - reuse) & 3], (uint32_t)((it - reuse) >> 2) & 1u, p.error_flag, 5);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+            if (probe) stamp[15] = clock64();
             // hi = raw fp32 (the tensor core truncates to TF32), lo = x - trunc_tf32(x). Single pass: round to nearest
             // instead (add half a TF32 ulp to the magnitude before the truncation) - truncation shrinks every product by
             // 2^-12 on average, a bias that does not average out over the ~1 200 terms of a sum.
@@ -265,8 +280,10 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (probe) stamp[16] = clock64();
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[it & 3]);   // 4 arrivals instead of 128: the arrive chain is on the critical path
+            if (probe) stamp[17] = clock64();
         }
         const int wq = warp - 2;
         const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split,

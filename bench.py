@@ -12,7 +12,7 @@ A "step" is one pass of the hot path over one batch. --config selects the worklo
   1  24 images of 512 x 768 per GPU and step, bin width 1                       (default: the headline)
   2  the same batch, bin widths delta x {1, 2, 4, 8} in turn (one EAE), rate / PSNR per delta against the oracle
   3  4096 images of 512 x 768 in all, sharded over the GPUs (32 per step); the step count follows from the workload
-  4  256 frames of 2160 x 3840 in all, sharded over the GPUs (whole-frame semantics, 4 frames per step)
+  4  256 frames of 2160 x 3840 in all, sharded over the GPUs (whole-frame semantics, 16 frames per step)
 
   value  images/s with the batch already resident in HBM (eae_compress_dev + eae_decompress_dev)
   e2e    the same through the public host API (Codec.compress / Codec.decompress) from pinned host
@@ -56,9 +56,9 @@ CONFIGS = {
                 'synthetic 512x768 luma images per GPU'},
     3: {'batch': 32, 'height': 512, 'width': 768, 'deltas': (1,), 'coder_lanes': 1, 'depth': 12, 'total': 4096,
         'name': 'configs[3]: 4096 synthetic 512x768 luma images in all, sharded over the GPUs, 32 per step'},
-    4: {'batch': 4, 'height': 2160, 'width': 3840, 'deltas': (1,), 'coder_lanes': 1, 'depth': 4, 'total': 256,
+    4: {'batch': 16, 'height': 2160, 'width': 3840, 'deltas': (1,), 'coder_lanes': 1, 'depth': 8, 'total': 256,
         'name': 'configs[4]: 256 synthetic 2160x3840 luma frames in all (whole-frame semantics, latent 135x240), sharded over '
-                'the GPUs, 4 per step'},
+                'the GPUs, 16 per step'},
 }
 
 
@@ -81,6 +81,8 @@ def parse_args():
                          'per GPU would otherwise spin on more threads than the box has cores); 0: driver default')
     ap.add_argument('--coder-lanes', type=int, default=None,
                     help='GPU threads per coded stream (0 = one warp per stream: lowest latency)')
+    ap.add_argument('--bin-widths', type=str, default=None,
+                    help='comma-separated bin-width multipliers out of 1, 2, 4, 8 (default: the config\'s)')
     ap.add_argument('--depth', type=int, default=None,
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')
     args = ap.parse_args()
@@ -90,7 +92,7 @@ def parse_args():
             setattr(args, key, cfg[key])
     if os.environ.get('EAE_PIPELINE_DEPTH'):
         args.depth = int(os.environ['EAE_PIPELINE_DEPTH'])
-    args.deltas = cfg['deltas']
+    args.deltas = tuple(int(x) for x in args.bin_widths.split(',')) if args.bin_widths else cfg['deltas']
     args.total = cfg['total']
     return args
 

@@ -115,6 +115,28 @@ def test_random_streams_against_the_oracle(core):
             assert err == 0 and numpy.array_equal(dec, x), trial
 
 
+def test_more_than_31_follow_bits_from_one_bin(core):
+    """Streams whose interval straddles the midpoint for dozens of E3 steps (BinaryArithmeticCoder.cpp:238-246), so that
+    one renormalisation releases a bit and 45 / 52 / 60 queued follow bits: more than one 32-bit put. Found by hill
+    climbing on a model of the coder's registers; every formulation must take its slow path and agree with the oracle."""
+    cases = [([0.5059247899741813, 0.1629641289648215, 0.05125147724638375],
+              [0, 1, 1, 3, 1, 1, 2, 1, 2, 1, 3, 3, 2, 2, 1, 3, 1, 3, 3, 1, 0, 0, 0, 1, 0, 3, 3, 0, 0, 1, 0, 3, 1, 0, 1, 3, 1, 0, 0, 2]),
+             ([0.6068877841736549, 0.37167546978247545, 0.32194534925419743],
+              [2, 0, 2, 0, 1, 0, 3, 1, 0, 2, 2, 3, 0, 2, 0, 1, 0, 0, 1, 0, 3, 1, 3, 3, 1, 3, 0, 0, 2, 0, 1, 0, 0, 0, 0, 2, 1, 1, 3, 1]),
+             ([0.0479767467199812, 0.468634543253395, 0.25753457899273247],
+              [2, 0, 3, 3, 2, 1, 3, 3, 2, 1, 1, 1, 1, 3, 1, 3, 3, 1, 1, 2, 1, 1, 2, 3, 3, 2, 1, 1, 3, 1, 1, 2, 1, 2, 0, 3, 3, 2, 3, 3])]
+    for (probs, magnitudes) in cases:
+        p = numpy.array(probs)
+        x = numpy.array(magnitudes, dtype=numpy.int16)
+        x[::3] *= -1
+        want = oracle_coder.encode_map(x, p, 'port')
+        got = encode(core, x, p)
+        assert want[0] == 0 and got[0] == 0 and (got[2], got[4]) == (want[2], want[4])
+        assert numpy.array_equal(got[1], want[1]) and numpy.array_equal(got[3], want[3])
+        (err, dec) = decode(core, x.size, p, want[1], want[2], want[3], want[4], 1)
+        assert err == 0 and numpy.array_equal(dec, x)
+
+
 def test_malformed_streams_decode_like_the_oracle(core):
     """Truncated / corrupted inputs: same error code and, when both succeed, the same symbols (stale-bit
     padding of BinaryArithmeticCoder.cpp:104-122, 275-315)."""

@@ -352,3 +352,35 @@ def test_device_entry_points_report_through_poll_status(native, golden):
     compress(bound)
     decompress(d_cont, bound)
     assert codec.poll_status()['code'] == 0 and numpy.array_equal(d_rec.cpu().numpy(), want_rec)
+
+
+def test_every_packing_of_the_coder_kernels_gives_the_same_container(native, golden):
+    """GPU threads per coded stream (eae_codec_set_coder_lanes): 1 = 32 streams per warp (branch-free formulation, the
+    bench's throughput setting), 2 / 4 = partial packing, 32 = one stream per warp (the scalar, branching formulation of
+    csrc/coder_core.cuh: the latency setting), 0 = automatic. Same bytes from all of them, every stream equal to the
+    reference coder on the same indices, exact round trip - on peaked and on wide symbol distributions (bin widths 1 and
+    1/8: long runs of truncated-unary bins and Exp-Golomb suffixes)."""
+    rng = numpy.random.default_rng(15)
+    w = visible_weights(6, False)
+    (n, h, wd) = (3, 128, 192)
+    lum = util.synthetic_luma(rng, n, h, wd)
+    for delta in (1., 0.125):
+        params = native_codec.CodingParams(delta*numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'),
+                                           0.05*golden.map_mean('1_10000'))
+        blobs = []
+        for lanes in (0, 1, 2, 4, 32):
+            codec = native_codec.Codec(w, False, math='mixed')
+            codec.set_coder_lanes(lanes)
+            blob = numpy.array(codec.compress(lum, params), copy=True)
+            idx = codec.last_indices(n, h, wd)
+            rec = numpy.array(codec.decompress(blob, params), copy=True)
+            assert numpy.array_equal(codec.last_indices(n, h, wd), idx), lanes       # the decoder inverts the encoder
+            blobs.append((blob, rec))
+        for (blob, rec) in blobs[1:]:
+            assert numpy.array_equal(blob, blobs[0][0]) and numpy.array_equal(rec, blobs[0][1])
+        (_, streams) = native_codec.parse_container(blobs[0][0])
+        flat = idx.reshape(n*128, -1)
+        for s in range(n*128):
+            want = oracle_coder.encode_map(flat[s], params.table[s % 128], WHICH)
+            assert want[0] == 0 and (streams[s][0], streams[s][1]) == (want[2], want[4]), (delta, s)
+            assert numpy.array_equal(streams[s][2], want[1]) and numpy.array_equal(streams[s][3], want[3]), (delta, s)
