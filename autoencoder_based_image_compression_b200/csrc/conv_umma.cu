@@ -309,7 +309,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * kStamps4 * sizeof(long long), st));
                 for (int i = 0; i < qx.n_phases; i++) qx.ph[i].times = d_times;
             }
-            kernel4<<<grid4, kUmmaThreads3, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
+            kernel4<<<grid4, kUmmaThreads4, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
             EAE_LAUNCH_OK();
             if (timing4) {
                 std::vector<long long> h((size_t)grid4 * kStamps4);

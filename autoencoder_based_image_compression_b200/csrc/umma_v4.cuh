@@ -33,6 +33,8 @@ constexpr int kSmemBytes4 = kOffBars4 + 512 + 1024;
 constexpr int kGdnStageBytes4 = 4 * kTileBytes;
 static_assert(3 * kGdnStageBytes4 <= kOffBars4, "GDN / epilogue stages must fit below the barriers");
 constexpr int kMaxGroups4 = 4;
+// warps: 0 TMA producer, 1 MMA issuer of half 0 (and of the fused tail), 2-9 conversion / epilogue, 10 MMA issuer of half 1
+constexpr int kUmmaThreads4 = 352;
 constexpr int kStamps4 = 24;     // clock stamps per CTA (EAE_UMMA_TIMING=4): [0..7] phases, [8..10] timer / SM, [12..21] iteration 8
 
 struct UmmaTap4 { int w_tap, off, grp, last; };            // off: row offset of this tap's box inside its group's union
@@ -63,6 +65,52 @@ struct UmmaParams4x {
     int n_phases, pad;
     UmmaParams4 ph[4];
 };
+
+// Main-loop MMA issue of half kHalf of the tile (its own warp). A tcgen05.mma occupies its issuing thread for about as
+// long as it executes (~68 cycles for M128 N128 K8, measured: the queue behind it is shallow), so with ONE issuer the
+// tensor pipe idled through that warp's barrier round trips of every iteration (~330 of 900 cycles in one pass, ~330 of
+// 1 960 in 3xTF32); with one issuer per half the other half's MMAs fill them. kHalf is a template argument so that every
+// operand stays a compile-time function of warp-uniform values (uniform-datapath issue, see the note on kTmemBase0).
+template <int kHalf>
+__device__ __forceinline__ bool mma_issue_loop4(const UmmaParams4& p, uint8_t* smem, uint64_t* split, uint64_t* done,
+                                                uint64_t* acc_full, int n_main, int lane, long long* stamp)
+{
+    bool ok = true;
+    for (int it = 0; it < n_main && ok; it++) {
+        const int slot_i = it & 1, s = it & 3;
+        const bool probe = stamp && it == 8 && lane == 0;
+        if (probe) stamp[18] = clock64();
+        // (every lane polls: with one polling lane and a shuffle the compiler no longer proves the MMA operands
+        //  warp-uniform and the issue of every tcgen05.mma slows down by ~25 cycles - measured)
+        ok = mbar_wait(&split[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
+        if (probe) { stamp[19] = clock64(); stamp[20] = stamp[19]; }
+        ok = __all_sync(0xFFFFFFFFu, ok);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint32_t st = smem_u32(smem + kOffB4 + s * kBStageBytes4);
+            // single pass: the lo columns of a set's slot are a second hi slot (iterations it, it + 2 of the set)
+            const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i +
+                                  (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
+            const uint32_t d = kTmemBase0 + (kHalf ? kCol3Acc1 : kCol3Acc0);
+            const uint32_t a_hi = slot + 64u * (uint32_t)kHalf, a_lo = a_hi + 32u;
+            #pragma unroll
+            for (int k = 0; k < kChunkK / 8; k++) {
+                const uint64_t b_hi = make_desc(st + k * 32);
+                umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
+                if (p.exact_main) {
+                    umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
+                    umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
+                }
+            }
+            umma_commit(&done[s]);
+            if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
+            if (probe) stamp[21] = clock64();
+        }
+        __syncwarp();
+    }
+    return ok;
+}
 
 // kPrecise: IEEE normalisation in the fused tail; kQuant: the store is the quantizer (OutGeom4::idx_out)
 template <bool kPrecise, bool kQuant>
@@ -110,11 +158,11 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 4; s++) mbar_init(&done[s], 1);
+        for (int s = 0; s < 4; s++) mbar_init(&done[s], 2);       // one commit per MMA-issuing warp
         for (int s = 0; s < 2; s++) mbar_init(&u_full[s], 1);
         for (int s = 0; s < 4; s++) mbar_init(&split[s], 5);      // one arrival per conversion warp + the producer's
         gdn_tail_ts_init(tail);
-        mbar_init(acc_full, 1);
+        mbar_init(acc_full, 2);                                   // (both issuers)
         mbar_init(nrm_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -175,47 +223,12 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
             if (ok && n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
-        {
-            bool ok = true;
-            for (int it = 0; it < n_main && ok; it++) {
-                const int slot_i = it & 1, s = it & 3;
-                const bool probe = stamp && it == 8 && lane == 0;
-                if (probe) stamp[18] = clock64();
-                // (every lane polls: with one polling lane and a shuffle the compiler no longer proves the MMA operands
-                //  warp-uniform and the issue of every tcgen05.mma slows down by ~25 cycles - measured)
-                ok = mbar_wait(&split[s], (uint32_t)(it >> 2) & 1u, p.error_flag, 1);
-                if (probe) { stamp[19] = clock64(); stamp[20] = stamp[19]; }
-                ok = __all_sync(0xFFFFFFFFu, ok);
-                if (!ok) break;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(smem + kOffB4 + s * kBStageBytes4);
-                    // single pass: the lo columns of a set's slot are a second hi slot (iterations it, it + 2 of the set)
-                    const uint32_t slot = kTmemBase0 + kCol3Slots + 128u * (uint32_t)slot_i +
-                                          (p.exact_main ? 0u : 32u * (uint32_t)((it >> 1) & 1));
-                    #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t d = kTmemBase0 + (h ? kCol3Acc1 : kCol3Acc0);
-                        const uint32_t a_hi = slot + 64u * (uint32_t)h, a_lo = a_hi + 32u;
-                        #pragma unroll
-                        for (int k = 0; k < kChunkK / 8; k++) {
-                            const uint64_t b_hi = make_desc(st + k * 32);
-                            umma_tf32_ts(d, a_hi + 8 * k, b_hi, (it == 0 && k == 0) ? 0u : 1u);
-                            if (p.exact_main) {
-                                umma_tf32_ts(d, a_lo + 8 * k, b_hi, 1u);
-                                umma_tf32_ts(d, a_hi + 8 * k, make_desc(st + kTileBytes + k * 32), 1u);
-                            }
-                        }
-                    }
-                    umma_commit(&done[s]);
-                    if (it == n_main - 1) { umma_commit(acc_full); if (stamp) stamp[3] = clock64(); }
-                    if (stamp && it == 8) stamp[21] = clock64();
-                }
-                __syncwarp();
-            }
-            if (ok && n_gdn) gdn_tail_ts_mma(tail, p.error_flag);
-        }
+        // ===== MMA issuers: the whole warp runs the loop, one elected lane issues. TWO warps, one per half of the tile
+        // (mma_issue_loop4): each accumulator is still fed by ONE thread in program order, so the result does not depend
+        // on how the two streams of MMAs interleave.
+        if (mma_issue_loop4<0>(p, smem, split, done, acc_full, n_main, lane, stamp) && n_gdn) gdn_tail_ts_mma(tail, p.error_flag);
+    } else if (warp == 10) {
+        mma_issue_loop4<1>(p, smem, split, done, acc_full, n_main, lane, nullptr);
     } else {
         // ===== warps 2..9: two conversion / epilogue sets; set k owns TMEM A slot k and the iterations of parity k
         const int quarter = warp & 3;
