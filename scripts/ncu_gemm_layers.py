@@ -45,21 +45,32 @@ def main():
                              'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'launch__registers_per_thread',
                              'launch__shared_mem_per_block_dynamic']}
     print('# ' + title + '\n')
-    print('Source: `ncu --set full --clock-control none --import-source on -k "regex:gemm_umma|tconv9s4" -s 13 -c 13` around '
-          '`python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline` on one B200, read with `ncu -i ... --page raw --csv` '
+    print('Source: `ncu --set full --clock-control none --import-source on -k "regex:gemm_umma|tconv9s4" -c 14` around '
+          '`python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-parity` on one B200, read with `ncu -i ... --page raw --csv` '
           '(`scripts/ncu_gemm_layers.py`). Durations under ncu are cold-cache and serialised (SM clock {} GHz in the capture); the '
           'bench line is the timing. One launch = one layer (or one output phase of a transposed convolution) over {} images of '
           '512 x 768.\n'.format(rows[2][c['sm__cycles_elapsed.avg.per_second']][:5], images))
+    body = rows[2:]
+    start = 0
+    stitched = False
+    for (k, r) in enumerate(body):          # a step starts right after the persistent last-layer kernel of the previous one
+        if 'umma7' in r[c['Kernel Name']]:
+            if k + 1 + len(NAMES) <= len(body):
+                start = k + 1
+            elif len(body) >= len(NAMES):
+                # the capture straddles two consecutive (identical) steps: the launches after the last layer, then the
+                # ones before it that complete the step
+                missing = len(NAMES) - (len(body) - (k + 1))
+                body = body[k + 1:] + body[k + 1 - missing:k + 1]
+                stitched = True
+            break
+    if stitched:
+        print('(The 14 captured launches straddle two consecutive steps of identical work: the first '
+              '{} rows of the table are from the later step, the rest from the one before it.)\n'.format(len(NAMES) - missing))
     print('| launch | kernel | grid | duration us | DRAM read MB | DRAM write MB | tensor sub-pipe active / (4 x SM cycles) | '
           'algorithmic TFLOP/s | executed-MMA TFLOP/s |')
     print('|---|---|---|---|---|---|---|---|---|')
     (tt, tr, tw, ta, te) = (0., 0., 0., 0., 0.)
-    body = rows[2:]
-    start = 0
-    for (k, r) in enumerate(body):          # a step starts right after the persistent last-layer kernel of the previous one
-        if 'umma7' in r[c['Kernel Name']] and k + 1 + len(NAMES) <= len(body):
-            start = k + 1
-            break
     for (k, r) in enumerate(body[start:start + len(NAMES)]):
         d = float(r[c['gpu__time_duration.sum']])
         rd = float(r[c['dram__bytes_read.sum']])
