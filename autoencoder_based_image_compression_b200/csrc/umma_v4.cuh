@@ -240,14 +240,20 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         const int row_in_union = (row >> 4) * kUnionW + (row & 15);     // half 1 adds 8 union rows
         bool ok = true;
         uint32_t r[32], hi[32];
+        int g_seen = -1;      // union this thread has already seen land (a completed-phase wait still costs ~80 cycles)
         for (int it = set; it < n_main && ok; it += 2) {
             const int kc = it / p.n_taps, t = it - kc * p.n_taps;
             const UmmaTap4 tap = p.taps[t];
             const int g = kc * p.n_groups + tap.grp;
             const bool probe = stamp && it == 8 && threadIdx.x == 64;
             if (probe) stamp[12] = clock64();
-            ok = mbar_wait(&u_full[g & 1], (uint32_t)(g >> 1) & 1u, p.error_flag, 2);
-            if (!ok) break;
+            if (g != g_seen) {
+                // (the buffer keeps union g until the MMAs of the group's last tap are done, i.e. past every conversion
+                //  of the group: one wait per union and thread is enough)
+                ok = mbar_wait(&u_full[g & 1], (uint32_t)(g >> 1) & 1u, p.error_flag, 2);
+                if (!ok) break;
+                g_seen = g;
+            }
             if (probe) stamp[13] = clock64();
             if (stamp && it == 0 && threadIdx.x == 64) stamp[2] = clock64();
             // Read both halves' rows first: the shared-memory reads do not depend on the TMEM slot, so they overlap the

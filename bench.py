@@ -11,8 +11,8 @@ A "step" is one pass of the hot path over one batch. --config selects the worklo
   0  one 512 x 768 image per step (latency case: one warp per coded stream), bin width 1
   1  24 images of 512 x 768 per GPU and step, bin width 1                       (default: the headline)
   2  the same batch, bin widths delta x {1, 2, 4, 8} in turn (one EAE), rate / PSNR per delta against the oracle
-  3  4096 images of 512 x 768 in all, sharded over the GPUs (32 per step); the step count follows from the workload
-  4  256 frames of 2160 x 3840 in all, sharded over the GPUs (whole-frame semantics, 16 frames per step)
+  3  4096 images of 512 x 768 in all, sharded over the GPUs (up to 32 per step); the step count follows from the workload
+  4  256 frames of 2160 x 3840 in all, sharded over the GPUs (whole-frame semantics, up to 16 frames per step)
 
   value  images/s with the batch already resident in HBM (eae_compress_dev + eae_decompress_dev)
   e2e    the same through the public host API (Codec.compress / Codec.decompress) from pinned host
@@ -55,10 +55,10 @@ CONFIGS = {
         'name': 'configs[2]: quantization sweep, one EAE, bin widths delta x {1, 2, 4, 8} on consecutive steps of 24 '
                 'synthetic 512x768 luma images per GPU'},
     3: {'batch': 32, 'height': 512, 'width': 768, 'deltas': (1,), 'coder_lanes': 1, 'depth': 12, 'total': 4096,
-        'name': 'configs[3]: 4096 synthetic 512x768 luma images in all, sharded over the GPUs, 32 per step'},
+        'name': 'configs[3]: 4096 synthetic 512x768 luma images in all, sharded over the GPUs, up to 32 per step'},
     4: {'batch': 16, 'height': 2160, 'width': 3840, 'deltas': (1,), 'coder_lanes': 1, 'depth': 8, 'total': 256,
         'name': 'configs[4]: 256 synthetic 2160x3840 luma frames in all (whole-frame semantics, latent 135x240), sharded over '
-                'the GPUs, 16 per step'},
+                'the GPUs, up to 16 per step'},
 }
 
 
@@ -87,6 +87,7 @@ def parse_args():
                     help='pipeline slots (CUDA streams) that consecutive steps rotate over')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    batch_given = args.batch is not None
     for key in ('batch', 'height', 'width', 'coder_lanes', 'depth'):
         if getattr(args, key) is None:
             setattr(args, key, cfg[key])
@@ -94,6 +95,11 @@ def parse_args():
         args.depth = int(os.environ['EAE_PIPELINE_DEPTH'])
     args.deltas = tuple(int(x) for x in args.bin_widths.split(',')) if args.bin_widths else cfg['deltas']
     args.total = cfg['total']
+    if args.total and not batch_given:
+        # a fixed job sharded over many ranks: keep at least 8 steps per rank, so that the pipeline slots have batches to
+        # overlap (the coder of a batch is a latency chain: 256 4K frames over 8 GPUs as 2 steps of 16 run at half the rate)
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        args.batch = max(1, min(args.batch, args.total//world//8))
     return args
 
 
@@ -163,6 +169,9 @@ def run_cpu_arm(args, steps, warmup, sample_per_core=1):
     sample = args.cpu_sample or max(4, int(min(cores, 32)*sample_per_core/max(1., scale)))
     which = 'ref' if coder.has_ref() else 'port'
     coder.build()
+    # (one call in this process as well: the workers that do the coding are forked and torn down, and whoever lists the
+    #  native libraries of the arm should see the coder's)
+    assert coder.compress_lossless(numpy.array([0, 1, -2, 2, 1, 0, 0, 0], dtype=numpy.int16), numpy.full(3, 0.5), which)[2] == 20
     weights = wts.random_init(0, False)
     images = synthetic.synthetic_luma(numpy.random.default_rng(1), sample, args.height, args.width)
     tables = [load_tables(d) for d in args.deltas]
@@ -201,7 +210,7 @@ class ClockSampler(object):
         self.gpu_index = gpu_index
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
-                                          '-i', str(gpu_index), '-lms', '100'],
+                                          '-i', str(gpu_index), '-lms', '20'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -500,10 +509,12 @@ def run_gpu_arm(args):
     # second one captures and instantiates the step graphs (csrc/codec.cu, run_as_step_graph), from the third on it
     # replays them: the timed region must not contain the 2 x depth graph instantiations.
     warmup_run = max(args.warmup, 2*depth)
+    # (the clock sampler starts before the warm-up: nvidia-smi needs ~0.1 s to come up and a 20-step region lasts 33 ms;
+    #  its samples under load are those of the warm-up and of the timed region, which run back to back)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(warmup_run):
         step_dev(i, slots[i % depth])
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.eae_launch_count()
     dev_ms = timed_dev(slots, steps, args.warmup, True)
     launches = lib.eae_launch_count() - launches0
