@@ -353,6 +353,24 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                                         "slot written %.0f, arrived %.0f | MMA warp: loop top %.0f, slot seen %.0f, weights seen %.0f, issued %.0f\n",
                                 cv[1] / nb, cv[2] / nb, cv[3] / nb, cv[4] / nb, cv[5] / nb, mm[0] / nb, mm[1] / nb, mm[2] / nb, mm[3] / nb);
                 }
+                if (q.fuse) {
+                    // the fused tail, cycles from the moment conversion warp 2 saw the accumulators complete
+                    double cv[11] = {0}, mm[8] = {0};
+                    uint32_t nb = 0;
+                    for (uint32_t b = 0; b < grid4; b++) {
+                        const long long* t = &h[(size_t)b * kStamps4];
+                        if (!t[4] || !t[24 + 10]) continue;
+                        nb++;
+                        for (int j = 0; j < 11; j++) cv[j] += (double)(t[24 + j] - t[4]);
+                        for (int j = 0; j < 8; j++) mm[j] += (double)(t[24 + 12 + j] - t[4]);
+                    }
+                    if (nb)
+                        fprintf(stderr, "umma4 tail (cycles from accumulators seen): conversions %.0f %.0f, x0 copied %.0f, conversions %.0f %.0f, "
+                                        "norm 0 seen %.0f, half 0 normalised %.0f, barrier %.0f, stored %.0f, half 1 staged %.0f | MMA steps issued "
+                                        "%.0f %.0f %.0f %.0f %.0f %.0f %.0f %.0f\n",
+                                cv[0] / nb, cv[1] / nb, cv[2] / nb, cv[3] / nb, cv[4] / nb, cv[5] / nb, cv[6] / nb, cv[7] / nb, cv[8] / nb, cv[10] / nb,
+                                mm[0] / nb, mm[1] / nb, mm[2] / nb, mm[3] / nb, mm[4] / nb, mm[5] / nb, mm[6] / nb, mm[7] / nb);
+                }
                 fprintf(stderr, "umma4 taps %d groups %d fuse %d grid %u: setup %.0f first_union %.0f acc_seen %.0f nrm_seen %.0f "
                                 "staged %.0f end %.0f (avg cycles from CTA start, conversion warp 2); CTA duration min %lld "
                                 "p10 %lld median %lld p90 %lld max %lld\n",
