@@ -69,6 +69,48 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
 }
 
 // uint8 image [n, H, W] -> boxes of kImgBoxW x kImgBoxH pixels of one image, no swizzle, zero fill outside.
+// Output map of a fused tile's TMA stores (OutGeom4::map_out, umma_v3.cuh): *use = false when this output geometry keeps
+// the per-warp stores (quantizer, parity-split phases, odd sizes, EAE_NO_TMA_STORE, or a driver that refuses the map).
+int make_out_map(CUtensorMap* map, const GemmPlan& plan, uint64_t n_img, bool* use)
+{
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("EAE_NO_TMA_STORE"); disabled = (e && atoi(e)) ? 1 : 0; }
+    *use = false;
+    if (disabled || !plan.fuse || plan.quant_idx || !plan.out) return 0;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return 0;
+    const uint64_t px = (uint64_t)kCout * sizeof(float);      // one pixel: 128 channels
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bdim[5], estride[5] = {1, 1, 1, 1, 1};
+    const void* base = plan.out;
+    int rank;
+    if (plan.out_split) {
+        // [n][plane (y & 1) * 2 + (x & 1)][Hout / 2][Wout / 2][128]; a tile row of the position grid alternates between two planes
+        if (plan.out_mul != 1 || (plan.Hout & 1) || (plan.Wout & 1) || plan.Hg != plan.Hout || plan.Wg != plan.Wout) return 0;
+        const uint64_t plane = (uint64_t)(plan.Hout / 2) * (uint64_t)(plan.Wout / 2) * px;
+        rank = 5;
+        gdim[0] = kCout; gdim[1] = 4; gdim[2] = (cuuint64_t)(plan.Wout / 2); gdim[3] = (cuuint64_t)(plan.Hout / 2); gdim[4] = n_img;
+        gstride[0] = plane; gstride[1] = px; gstride[2] = (uint64_t)(plan.Wout / 2) * px; gstride[3] = 4 * plane;
+        bdim[0] = 32; bdim[1] = 2; bdim[2] = 8; bdim[3] = 4; bdim[4] = 1;
+    } else {
+        // position (a, b) -> pixel (a * out_mul + out_r, b * out_mul + out_s): a strided view from the phase's first pixel
+        const int m = plan.out_mul;
+        if (m < 1 || plan.out_r >= plan.Hout || plan.out_s >= plan.Wout) return 0;
+        const int wv = (plan.Wout - plan.out_s + m - 1) / m, hv = (plan.Hout - plan.out_r + m - 1) / m;
+        base = plan.out + ((size_t)plan.out_r * plan.Wout + (size_t)plan.out_s) * kCout;
+        rank = 4;
+        gdim[0] = kCout; gdim[1] = (cuuint64_t)(wv < plan.Wg ? wv : plan.Wg); gdim[2] = (cuuint64_t)(hv < plan.Hg ? hv : plan.Hg);
+        gdim[3] = n_img;
+        gstride[0] = (uint64_t)m * px; gstride[1] = (uint64_t)m * (uint64_t)plan.Wout * px;
+        gstride[2] = (uint64_t)plan.Hout * (uint64_t)plan.Wout * px;
+        bdim[0] = 32; bdim[1] = 16; bdim[2] = 8; bdim[3] = 1;
+    }
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim,
+                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    *use = r == CUDA_SUCCESS;
+    return 0;
+}
 int make_map_u8(CUtensorMap* map, const void* base, uint64_t W, uint64_t H, uint64_t n)
 {
     EncodeTiledFn fn = encode_tiled_fn();
@@ -282,9 +324,16 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_TRY(make_map(&map_g_hi, gamma->hi, 3, gdims, bbox));
                 EAE_TRY(make_map(&map_g_lo, gamma->lo, 3, gdims, bbox));
             }
+            OutMaps4 maps_out;
+            memset(&maps_out, 0, sizeof maps_out);
+            for (int ph = 0; ph < qx.n_phases; ph++) {
+                bool use = false;
+                EAE_TRY(make_out_map(&maps_out.m[ph], ph ? more[ph - 1] : plan, n_img, &use));
+                qx.ph[ph].tma_out = use ? 1 : 0;
+            }
             // four instantiations: {MUFU, IEEE} normalisation x {fp32 pixels, quantizer} store
             typedef void (*Kernel4)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                                    const UmmaParams4x);
+                                    const OutMaps4, const UmmaParams4x);
             static const Kernel4 kernels4[4] = {gemm_umma4_kernel<false, false>, gemm_umma4_kernel<true, false>,
                                                 gemm_umma4_kernel<false, true>, gemm_umma4_kernel<true, true>};
             static bool attr4_done = false;
@@ -309,7 +358,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                 EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid4 * kStamps4 * sizeof(long long), st));
                 for (int i = 0; i < qx.n_phases; i++) qx.ph[i].times = d_times;
             }
-            kernel4<<<grid4, kUmmaThreads4, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, qx);
+            kernel4<<<grid4, kUmmaThreads4, kSmemBytes4, st>>>(map_u, map_b_hi, map_b_lo, map_g_hi, map_g_lo, maps_out, qx);
             EAE_LAUNCH_OK();
             if (timing4) {
                 std::vector<long long> h((size_t)grid4 * kStamps4);
@@ -415,8 +464,14 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             q.conv1 = 1;
             EAE_TRY(make_map_u8(&map_img, plan.img_u8, (uint64_t)plan.img_W, (uint64_t)plan.img_H, n_img));
         }
+        CUtensorMap map_out = map_b_hi;
+        {
+            bool use = false;
+            EAE_TRY(make_out_map(&map_out, plan, n_img, &use));
+            q.tma_out = use ? 1 : 0;
+        }
         typedef void (*Kernel3)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                                const CUtensorMap, const UmmaParams3);
+                                const CUtensorMap, const CUtensorMap, const UmmaParams3);
         static const Kernel3 kernels3[3] = {gemm_umma3_kernel<false, false>, gemm_umma3_kernel<true, false>,
                                             gemm_umma3_kernel<false, true>};
         static bool attr3_done = false;
@@ -433,7 +488,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
             EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid3 * 8 * sizeof(long long)));
             EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid3 * 8 * sizeof(long long), st));
             q.times = d_times;
-            kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
+            kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, map_out, q);
             EAE_LAUNCH_OK();
             std::vector<long long> h((size_t)grid3 * 8);
             EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -453,7 +508,7 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
                     acc[5] / grid3, acc[6] / grid3, acc[7] / grid3);
             return 0;
         }
-        kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, q);
+        kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, map_out, q);
         EAE_LAUNCH_OK();
         return 0;
     }

@@ -81,6 +81,23 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
           "r"(c3), "r"(c4)
         : "memory");
 }
+// Bulk tensor stores, shared -> global (bulk async-group completion): the writing threads make their generic-proxy
+// shared-memory writes visible to the async proxy (tma_store_fence), synchronise, then ONE thread issues the stores and
+// commits the group; before the CTA may exit (or the source is rewritten) that thread waits until the source has been read.
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
 {
     asm volatile(
@@ -157,6 +174,7 @@ struct UmmaParams3 {
     const float* dq_delta;   // [128]
     int hw_in;
     int Hout, Wout, out_mul, out_r, out_s, out_split;
+    int tma_out;             // fused tiles leave through TMA stores (the kernel's map_out; see OutGeom4)
     int mode;                // EpilogueMode of a standalone launch
     int fuse;                // 0 none, 1 GDN, 2 IGDN after the contraction
     int exact_main;          // 3xTF32 for the main contraction

@@ -51,11 +51,13 @@ struct UmmaParams4 {
     const float* q_mean;
     const float* q_delta;
     uint32_t* q_flag;
+    int tma_out;              // the phase's tiles leave through TMA stores (OutMaps4, OutGeom4::map_out)
     long long* times;
     uint32_t* error_flag;
     UmmaTap4 taps[kMaxTaps];
     UmmaGroup4 groups[kMaxGroups4];
 };
+struct OutMaps4 { CUtensorMap m[4]; };      // output map of each phase of a merged launch
 
 // Up to four launches that read the same input through the same weight array (the four output phases of a transposed
 // convolution) run as ONE grid: CTA b works on tile b / n_phases of phase b % n_phases. The phases of a tile are neighbours
@@ -117,9 +119,11 @@ template <bool kPrecise, bool kQuant>
 __global__ void __maxnreg__(kMaxRegs34)
 gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_b_hi,
                   const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_g_hi,
-                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ UmmaParams4x pp)
+                  const __grid_constant__ CUtensorMap map_g_lo, const __grid_constant__ OutMaps4 maps_out,
+                  const __grid_constant__ UmmaParams4x pp)
 {
     const UmmaParams4& p = pp.ph[blockIdx.x % (unsigned)pp.n_phases];
+    const CUtensorMap* map_out = p.tma_out ? &maps_out.m[blockIdx.x % (unsigned)pp.n_phases] : nullptr;
     const int tile_linear = (int)(blockIdx.x / (unsigned)pp.n_phases);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST
@@ -138,7 +142,8 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     uint64_t* acc_full = bars + 16;
     uint64_t* nrm_full = bars + 17;
     const GdnTailTs tail{smem, bars + 18 /* g_full[4] */, bars + 22 /* x_ready[4] */, bars + 26 /* x_free[4] */,
-                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn};
+                         bars + 30 /* acc0_read */, acc_full, bars + 31 /* nrm0_full */, nrm_full, p.exact_gdn,
+                         bars + 36 /* out_ready[4] */};
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +225,14 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
                 tma_load_3d(st, &map_b_hi, &split[s], kc * kChunkK, 0, tap.w_tap);
                 if (p.exact_main) tma_load_3d(st + kTileBytes, &map_b_lo, &split[s], kc * kChunkK, 0, tap.w_tap);
             }
-            if (ok && n_gdn) gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
+            if (ok && n_gdn) {
+                gdn_tail_ts_producer(tail, &map_g_hi, &map_g_lo, p.error_flag);
+                if (map_out && !kQuant) {
+                    const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split,
+                                        nullptr, nullptr, nullptr, nullptr, map_out};
+                    gdn_tail_ts_store_issuer(tail, geom, p.error_flag);
+                }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuers: the whole warp runs the loop, one elected lane issues. TWO warps, one per half of the tile
@@ -306,7 +318,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         }
         const int wq = warp - 2;
         const OutGeom4 geom{p.out, img, a0, b0, p.Hg, p.Wg, p.Hout, p.Wout, p.out_mul, p.out_r, p.out_s, p.out_split,
-                            p.idx_out, p.q_mean, p.q_delta, p.q_flag};
+                            p.idx_out, p.q_mean, p.q_delta, p.q_flag, map_out};
         uint8_t* stage0 = smem;                          // un-fused epilogue: both halves staged side by side
         uint8_t* stage1 = smem + kGdnStageBytes4;
         if (ok && n_gdn) {
