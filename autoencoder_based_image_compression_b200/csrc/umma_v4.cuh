@@ -163,8 +163,16 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
     const int a0 = (trem / p.tiles_x) * 16, b0 = (trem % p.tiles_x) * 16;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < 4; s++) mbar_init(&done[s], 2);       // one commit per MMA-issuing warp
+        // The first two union boxes are requested before anything else: they take 2-4 k cycles to arrive and need only
+        // their own two barriers; the other ~40 initialisations (~20 cycles each) then run under that latency.
         for (int s = 0; s < 2; s++) mbar_init(&u_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int u = 0; u < 2; u++) {      // (kchunks * n_groups >= 4 unions per tile)
+            const UmmaGroup4 grp = p.groups[u % p.n_groups];
+            mbar_expect_tx(&u_full[u], kUnionTx);
+            tma_load_5d(smem + u * kUnionBytes, &map_u, &u_full[u], (u / p.n_groups) * kChunkK, b0 + grp.fx, a0 + grp.fy, grp.plane, img);
+        }
+        for (int s = 0; s < 4; s++) mbar_init(&done[s], 2);       // one commit per MMA-issuing warp
         for (int s = 0; s < 4; s++) mbar_init(&split[s], 5);      // one arrival per conversion warp + the producer's
         gdn_tail_ts_init(tail);
         mbar_init(acc_full, 2);                                   // (both issuers)
@@ -194,7 +202,7 @@ gemm_umma4_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_consta
         // ===== TMA producer =====
         if (lane == 0) {
             bool ok = true;
-            int issued = 0;                       // unions requested so far
+            int issued = 2;                       // unions requested so far (the first two before the start barrier)
             for (int it = 0; it < n_main && ok; it++) {
                 const int kc = it / p.n_taps, t = it - kc * p.n_taps;
                 const UmmaTap4 tap = p.taps[t];
