@@ -581,8 +581,13 @@ def run_gpu_arm(args):
         return parallel.max_over_ranks(1e3*(time.perf_counter() - t0))
 
     timed_e2e(max(args.warmup, depth), 0)
-    blob_bytes = [0]*depth
-    e2e_ms = timed_e2e(steps, args.warmup)
+    # Three timed repetitions of the same K steps, the median reported (all three listed): the region is host-paced - 12
+    # Python threads over 35-150 ms of wall clock - and about one run in fifteen lost 2-3x to a single hiccup of the box.
+    e2e_runs = []
+    for rep in range(3):
+        blob_bytes = [0]*depth
+        e2e_runs.append(timed_e2e(steps, args.warmup))
+    e2e_ms = sorted(e2e_runs)[1]
     per_step_blob = sum(blob_bytes)//max(1, steps)
     h2d = batch_bytes + per_step_blob
     d2h = per_step_blob + batch_bytes + 8 + 8 + ctypes.sizeof(_native.BatchStats)
@@ -618,7 +623,9 @@ def run_gpu_arm(args):
         'gpu_launches': int(launches),
         'e2e': {'value': images_total/(e2e_ms/1e3), 'unit': 'images/s',
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step_wall': e2e_ms/steps, 'host_threads': depth},
+                'ms_per_step_wall': e2e_ms/steps, 'host_threads': depth,
+                'repetitions_images_per_s': [images_total/(t/1e3) for t in e2e_runs],
+                'note': 'median of three timed repetitions of the same {} steps (wall clock, max over ranks)'.format(steps)},
         'serial': {'value': n*serial_steps/(serial_ms/1e3), 'ms_per_step': serial_ms/serial_steps,
                    'note': 'same steps on one stream, one batch at a time (batch latency)'},
         'latency_ms': serial_ms/serial_steps,
