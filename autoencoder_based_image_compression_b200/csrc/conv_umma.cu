@@ -564,8 +564,9 @@ int launch_tconv9s4_fused(const float* in, const UmmaWeights& w, uint8_t* out_u8
 
 namespace {
 
-// Debug hook: sqrt_rn_norm / div_rn_norm against the compiler's IEEE sqrt.rn / div.rn.
-//   square roots: EVERY float in [2^-20, 2^40] (a norm + beta lies in [2e-5, ~1e6])
+// Debug hook: sqrt_rn_norm / div_rn_norm and the packed norm_apply2 against the compiler's IEEE sqrt.rn / div.rn / mul.rn.
+//   square roots: EVERY float in [2^-20, 2^40] (a norm + beta lies in [2e-5, ~1e6]), each also through the packed GDN and
+//   IGDN normalisation with two pseudo-random x
 //   quotients:    n_pairs pseudo-random pairs, |a| in [2^-30, 2^30] (either sign), b in [2^-10, 2^20]
 __global__ void norm_arith_check_kernel(uint64_t n_pairs, unsigned long long* __restrict__ bad)
 {
@@ -574,7 +575,18 @@ __global__ void norm_arith_check_kernel(uint64_t n_pairs, unsigned long long* __
     const uint32_t lo = 0x35800000u /* 2^-20 */, hi = 0x53800000u /* 2^40 */;
     for (uint64_t b = lo + tid; b <= hi; b += nth) {
         const float n = __uint_as_float((uint32_t)b);
-        if (__float_as_uint(sqrt_rn_norm(n)) != __float_as_uint(__fsqrt_rn(n))) bad_sqrt++;
+        const float s = __fsqrt_rn(n);
+        if (__float_as_uint(sqrt_rn_norm(n)) != __float_as_uint(s)) bad_sqrt++;
+        // the packed (fp32x2) normalisation of the fused tails against the compiler's IEEE operations: two pseudo-random
+        // x per n, |x| in [2^-30, 2^30], either sign, as a GDN (x / sqrt(n)) and as an IGDN (x * sqrt(n))
+        uint64_t z = b * 0x9E3779B97F4A7C15ull + 0x7654321ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const uint32_t u0 = (uint32_t)z, u1 = (uint32_t)(z >> 32);
+        const float x0 = __uint_as_float((u0 & 0x807FFFFFu) | ((127u - 30u + (u0 >> 23) % 61u) << 23));
+        const float x1 = __uint_as_float((u1 & 0x807FFFFFu) | ((127u - 30u + (u1 >> 23) % 61u) << 23));
+        const float2 g = norm_apply2<true>(x0, x1, n, n, 1), ig = norm_apply2<true>(x0, x1, n, n, 2);
+        if (__float_as_uint(g.x) != __float_as_uint(__fdiv_rn(x0, s)) || __float_as_uint(g.y) != __float_as_uint(__fdiv_rn(x1, s))) bad_div++;
+        if (__float_as_uint(ig.x) != __float_as_uint(__fmul_rn(x0, s)) || __float_as_uint(ig.y) != __float_as_uint(__fmul_rn(x1, s))) bad_sqrt++;
     }
     for (uint64_t i = tid; i < n_pairs; i += nth) {
         uint64_t z = i * 0x9E3779B97F4A7C15ull + 0x1234567ull;      // splitmix64

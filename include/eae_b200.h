@@ -393,8 +393,9 @@ int eae_codec_poll_status(eae_codec_t* codec, void* stream, eae_codec_status_t* 
 int eae_last_indices_host(eae_codec_t* codec, int16_t* idx_planar_out, uint64_t n_elems);
 
 /* Debug hook: the correctly rounded square root and quotient the fused GDN / IGDN normalisation uses
- * (tfutils.py:394-397, 506-509) against the compiler's sqrt.rn / div.rn: every float in [2^-20, 2^40] for the
- * square root, n_pairs pseudo-random pairs for the quotient. Both counts must be 0. */
+ * (tfutils.py:394-397, 506-509) against the compiler's sqrt.rn / div.rn: every float n in [2^-20, 2^40] for the
+ * square root - each also through the packed (fp32x2) x / sqrt(n) and x * sqrt(n) of the fused tails with two
+ * pseudo-random x -, n_pairs pseudo-random pairs for the scalar quotient. Both counts must be 0. */
 int eae_debug_check_norm_arithmetic(uint64_t n_pairs, uint64_t* sqrt_mismatches, uint64_t* div_mismatches);
 
 #ifdef __cplusplus

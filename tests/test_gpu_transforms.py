@@ -206,8 +206,9 @@ def test_random_shapes_against_the_oracle(native):
 
 def test_fused_normalisation_uses_correctly_rounded_sqrt_and_division(native):
     """tfutils.py:394-397, 506-509 divide by / multiply with sqrt(norm + beta). The fused GDN / IGDN epilogues use inlined
-    fast paths of the IEEE sequences (csrc/umma_v3.cuh, sqrt_rn_norm / div_rn_norm); they must be bit-equal to sqrt.rn /
-    div.rn for every float a norm can be (exhaustive over [2^-20, 2^40]) and on 2^32 pseudo-random quotients."""
+    fast paths of the IEEE sequences (csrc/umma_v3.cuh, sqrt_rn_norm / div_rn_norm, and their packed fp32x2 form
+    norm_apply2); they must be bit-equal to sqrt.rn / div.rn / mul.rn for every float a norm can be (exhaustive over
+    [2^-20, 2^40], two operands each) and on 2^32 pseudo-random quotients."""
     import ctypes
     (bad_sqrt, bad_div) = (ctypes.c_uint64(1), ctypes.c_uint64(1))
     native.check(native.lib().eae_debug_check_norm_arithmetic(1 << 32, ctypes.byref(bad_sqrt), ctypes.byref(bad_div)))
