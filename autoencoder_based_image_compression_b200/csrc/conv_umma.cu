@@ -73,8 +73,8 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
 // the per-warp stores (quantizer, parity-split phases, odd sizes, EAE_NO_TMA_STORE, or a driver that refuses the map).
 int make_out_map(CUtensorMap* map, const GemmPlan& plan, uint64_t n_img, bool* use)
 {
-    static int disabled = -1;
-    if (disabled < 0) { const char* e = getenv("EAE_NO_TMA_STORE"); disabled = (e && atoi(e)) ? 1 : 0; }
+    const char* env = getenv("EAE_NO_TMA_STORE");      // (read per launch: the tests switch it inside one process)
+    const bool disabled = env && atoi(env);
     *use = false;
     if (disabled || !plan.fuse || plan.quant_idx || !plan.out) return 0;
     EncodeTiledFn fn = encode_tiled_fn();

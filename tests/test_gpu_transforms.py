@@ -215,6 +215,32 @@ def test_fused_normalisation_uses_correctly_rounded_sqrt_and_division(native):
     assert (bad_sqrt.value, bad_div.value) == (0, 0)
 
 
+def test_tma_stores_of_the_fused_tiles_equal_the_per_warp_stores(native, golden, monkeypatch):
+    """The fused conv+GDN / tconv+IGDN tiles leave through TMA stores (natural, output-phase and parity-split maps; the
+    one-pass tail stages half 1 in the gaps of gamma); EAE_NO_TMA_STORE=1 keeps the per-warp stores. Same latent, same
+    float reconstruction, same container, bit for bit - for both arithmetic modes of the tensor path, both variants, and
+    grids that are not multiples of a tile (the maps clip what the per-warp stores predicate)."""
+    rng = numpy.random.default_rng(21)
+    mean = (0.05*golden.map_mean('1_10000')).astype(numpy.float32)
+    params = native_codec.CodingParams(numpy.ones(128, dtype=numpy.float32), golden.table('1_10000', '1'), mean)
+    for learned in (False, True):
+        w = visible_weights(6, learned)
+        for (n, h, wd) in ((3, 128, 192), (1, 48, 80), (2, 16, 272), (1, 400, 16), (1, 512, 768)):
+            lum = util.synthetic_luma(rng, n, h, wd)
+            for math in ('mixed', 'tf32x3'):
+                monkeypatch.delenv('EAE_NO_TMA_STORE', raising=False)
+                tma = native_codec.Codec(w, learned, math=math)
+                y = numpy.array(tma.encode(lum[..., None]), copy=True)
+                rec = numpy.array(tma.decode_float(y), copy=True)
+                blob = numpy.array(tma.compress(lum, params), copy=True)
+                monkeypatch.setenv('EAE_NO_TMA_STORE', '1')
+                warp = native_codec.Codec(w, learned, math=math)
+                assert numpy.array_equal(warp.encode(lum[..., None]), y), (learned, n, h, wd, math)
+                assert numpy.array_equal(warp.decode_float(y), rec), (learned, n, h, wd, math)
+                assert numpy.array_equal(warp.compress(lum, params), blob), (learned, n, h, wd, math)
+    monkeypatch.delenv('EAE_NO_TMA_STORE', raising=False)
+
+
 def test_fused_quantizer_and_dequantizer_equal_the_separate_launches(native, golden, monkeypatch):
     """The quantizer in the store of the last analysis layer (planar int16 straight from the GDN3 epilogue) and the
     dequantizer in the operand load of IGDN4 against the separate quantize / dequantize launches (EAE_NO_FUSE_QUANT=1):
