@@ -485,27 +485,34 @@ int launch_gemm_umma(const GemmPlan& plan, const UmmaWeights& w, const UmmaWeigh
         if (timing) {
             // Debug: per-CTA phase stamps, averaged over the grid, printed to stderr (synchronises the stream).
             long long* d_times = nullptr;
-            EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid3 * 8 * sizeof(long long)));
-            EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid3 * 8 * sizeof(long long), st));
+            EAE_CUDA_OK(cudaMalloc(&d_times, (size_t)grid3 * kStamps3 * sizeof(long long)));
+            EAE_CUDA_OK(cudaMemsetAsync(d_times, 0, (size_t)grid3 * kStamps3 * sizeof(long long), st));
             q.times = d_times;
             kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, map_out, q);
             EAE_LAUNCH_OK();
-            std::vector<long long> h((size_t)grid3 * 8);
+            std::vector<long long> h((size_t)grid3 * kStamps3);
             EAE_CUDA_OK(cudaMemcpyAsync(h.data(), d_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
             EAE_CUDA_OK(cudaStreamSynchronize(st));
             cudaFree(d_times);
             for (uint32_t b = 0; b < grid3; b += (grid3 / 3 ? grid3 / 3 : 1))
-                fprintf(stderr, "  cta %u raw: %lld | +%lld +%lld +%lld +%lld +%lld +%lld +%lld\n", b, h[(size_t)b * 8],
-                        h[(size_t)b * 8 + 1] - h[(size_t)b * 8], h[(size_t)b * 8 + 2] - h[(size_t)b * 8], h[(size_t)b * 8 + 3] - h[(size_t)b * 8],
-                        h[(size_t)b * 8 + 4] - h[(size_t)b * 8], h[(size_t)b * 8 + 5] - h[(size_t)b * 8], h[(size_t)b * 8 + 6] - h[(size_t)b * 8],
-                        h[(size_t)b * 8 + 7] - h[(size_t)b * 8]);
+                fprintf(stderr, "  cta %u raw: %lld | +%lld +%lld +%lld +%lld +%lld +%lld +%lld\n", b, h[(size_t)b * kStamps3],
+                        h[(size_t)b * kStamps3 + 1] - h[(size_t)b * kStamps3], h[(size_t)b * kStamps3 + 2] - h[(size_t)b * kStamps3], h[(size_t)b * kStamps3 + 3] - h[(size_t)b * kStamps3],
+                        h[(size_t)b * kStamps3 + 4] - h[(size_t)b * kStamps3], h[(size_t)b * kStamps3 + 5] - h[(size_t)b * kStamps3], h[(size_t)b * kStamps3 + 6] - h[(size_t)b * kStamps3],
+                        h[(size_t)b * kStamps3 + 7] - h[(size_t)b * kStamps3]);
             double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (uint32_t b = 0; b < grid3; b++)
-                for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * 8 + j] - h[(size_t)b * 8]);
+                for (int j = 1; j < 8; j++) acc[j] += (double)(h[(size_t)b * kStamps3 + j] - h[(size_t)b * kStamps3]);
             fprintf(stderr, "umma3 taps %d kchunks %d fuse %d conv1 %d grid %u: setup %.0f first_full %.0f main_issued %.0f acc_seen %.0f "
                             "nrm_seen %.0f staged %.0f end %.0f (avg cycles from CTA start)\n",
                     q.n_taps, q.kchunks, q.fuse, q.conv1, grid3, acc[1] / grid3, acc[2] / grid3, acc[3] / grid3, acc[4] / grid3,
                     acc[5] / grid3, acc[6] / grid3, acc[7] / grid3);
+            if (q.fuse && q.tma_out) {      // the store issuer (producer thread): cycles from CTA start
+                double is[6] = {0, 0, 0, 0, 0, 0};
+                for (uint32_t b = 0; b < grid3; b++)
+                    for (int j = 0; j < 6; j++) is[j] += (double)(h[(size_t)b * kStamps3 + 8 + j] - h[(size_t)b * kStamps3]);
+                fprintf(stderr, "umma3 store issuer: rounds seen ready %.0f %.0f %.0f %.0f, last stores issued %.0f, sources read %.0f\n",
+                        is[0] / grid3, is[1] / grid3, is[2] / grid3, is[3] / grid3, is[4] / grid3, is[5] / grid3);
+            }
             return 0;
         }
         kernel3<<<grid3, kUmmaThreads3, kSmemBytes3, st>>>(map_a, map_b_hi, map_b_lo, map_g_hi, map_g_lo, map_img, map_out, q);
