@@ -147,6 +147,10 @@ def lib():
         if not os.path.isfile(path):
             raise RuntimeError('{} is missing: run `python -m autoencoder_based_image_compression_b200.build` '
                                '(or __graft_entry__.build()). There is no CPU fallback.'.format(path))
+        # Every kernel of the library is loaded when its module is (CUDA's default loads a kernel at its first launch,
+        # which here would happen in the middle of twelve concurrent pipeline slots); no effect if the process has
+        # already initialised CUDA.
+        os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
         handle = ctypes.CDLL(path)
         for (name, (restype, argtypes)) in PROTOTYPES.items():
             fn = getattr(handle, name)

@@ -16,7 +16,12 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                 // fp32 elements per 128-byte swizzle row
 constexpr int kTileBytes = kTileM * 128;    // 16 KB: 128 rows x 128 bytes
 constexpr uint32_t kTmemCols2 = 512;              // every kernel here owns the whole TMEM of its SM (one CTA per SM)
-constexpr long long kTimeoutCycles = 400ll * 1000 * 1000;   // ~0.2 s
+// A barrier wait gives up after ~2 s. (It was 0.2 s until one bench run in about sixty, the first process on a fresh box,
+// reported a time-out of all three main-loop roles of a CTA in the middle of an otherwise normal run, while 4 800 steps of
+// scripts/soak.py and every other run passed: with the kernels of the library still being loaded lazily and twelve
+// streams of graph instantiations in flight, a running CTA can apparently be held for longer than that. A genuine
+// dead-lock is still reported, ten times later.)
+constexpr long long kTimeoutCycles = 4000ll * 1000 * 1000;
 
 struct UmmaTap { int plane, fy, fx, w_tap; };
 

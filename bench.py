@@ -512,6 +512,10 @@ def run_gpu_arm(args):
     # (the clock sampler starts before the warm-up: nvidia-smi needs ~0.1 s to come up and a 20-step region lasts 33 ms;
     #  its samples under load are those of the warm-up and of the timed region, which run back to back)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    # (one step on one slot alone first: whatever the first launch of each kernel costs - module loading, attribute calls,
+    #  the error-flag allocation - happens before twelve slots run beside each other)
+    step_dev(0, slots[0])
+    barrier()
     for i in range(warmup_run):
         step_dev(i, slots[i % depth])
     barrier()
